@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Fusion-decoder benchmark (BASELINE.json metric: fusion-decoder samples/s, 900 queries, 6 cameras).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+One "step" = one pass of the whole hot path (``Detr3DHead.forward``: 6 decoder layers + radar encoders + 3 radar
+layers + final heads) over one synthetic batch.  Workload at N=1 = BASELINE.json configs[1]: the res101 fusion head,
+batch 8, bf16 kernels.  N>1 (torchrun): weak scaling, every rank owns its own batch of 8, no data-path collective;
+the timing is the max over ranks.  ``value`` has the inputs resident in HBM; ``e2e`` goes through the plugin call
+with pinned HOST buffers (features, lidar2img, radar tokens) and reads the result back, both copies inside the
+timed region.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fusion_decoder_samples_per_s"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU")
+    ap.add_argument("--config", default="res101", choices=["res101", "vovnet", "tiny"])
+    ap.add_argument("--cpu-samples", type=int, default=8, help="bounded CPU-baseline sample (oracle forwards)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {"workload": f"TransCAR fusion head ({args.config} FPN shapes), batch {args.batch}/GPU, 900 queries, 6 cams, "
+                        f"4 levels x 256 ch, ~1.46k radar points, 6 decoder + 3 radar layers",
+            "batch_per_gpu": args.batch, "queries": 900, "cams": 6, "radar_slots": 1500, "feature_config": args.config,
+            "precision": args.precision, "parallelism": f"dp{args.gpus} (batch-sharded, no data-path collective)",
+            "l2_policy": "inputs larger than L2 (feature maps 757 MB bf16 per batch of 8 vs 126 MB L2) + L2 flush "
+                         "(256 MB write) between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def cpu_reference_pass(sd, feats, metas):
+    """One sample through the oracle = the reference's own CPU PyTorch path restated (oracle/fusion_decoder.py)."""
+    import torch
+    from oracle import fusion_decoder as O
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return O.head_forward(sd, feats, metas)
+
+
+def cpu_baseline(args, n_samples):
+    """Bounded sample: `n_samples` batch-1 forwards of the same workload on the host cores."""
+    import torch
+    from transcar_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic.make_state_dict(seed=0, num_query=900)
+    feats = synthetic.make_feats(0, 1, args.config)
+    metas = synthetic.make_img_metas(1, seed=0)
+    for _ in range(2):
+        cpu_reference_pass(sd, feats, metas)
+    times = []
+    for _ in range(n_samples):
+        t0 = time.perf_counter()
+        cpu_reference_pass(sd, feats, metas)
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return {"value": 1.0 / mean, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_samples} batch-1 forwards of the {args.config} fusion head (reference radar block is batch-1 only), "
+                      f"fp32, best {1.0 / min(times):.2f} samples/s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU path (oracle port; the reference is Python and its deps -
+    mmcv/mmdet/nuscenes-devkit - are not installable offline), all host threads, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from transcar_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic.make_state_dict(seed=0, num_query=900)
+    feats = synthetic.make_feats(0, 1, args.config)
+    metas = synthetic.make_img_metas(1, seed=0)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_pass(sd, feats, metas)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_pass(sd, feats, metas)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = 1.0 / dt
+    cfg = workload_config(args)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "each step = 1 sample (batch 1) of the same workload on the host cores"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from transcar_b200 import _lib, plugin, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    assert lib.tc_check_device() == 0, lib.tc_last_error_string().decode()
+
+    B, cfgname = args.batch, args.config
+    head_cfg = synthetic.head_config(900)
+    head_cfg["precision"] = args.precision
+    head = plugin.build_head(head_cfg)
+    head.load_state_dict(synthetic.make_state_dict(seed=0, num_query=900), strict=True)
+    head = head.cuda().eval()
+    eng = head.engine()
+    fdtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
+
+    # each rank owns its own batch (different seeds): weak scaling over samples
+    host_feats = [f.to(fdtype).permute(0, 1, 3, 4, 2).contiguous().pin_memory().permute(0, 1, 4, 2, 3)
+                  for f in synthetic.make_feats(rank, B, cfgname, smooth=False)]
+    metas = synthetic.make_img_metas(B, seed=rank)
+    dev_feats = [f.to(dev) for f in host_feats]
+    prepared = eng.prepare_inputs(dev_feats, metas)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return eng.forward_prepared(prepared)
+
+    def step_e2e():
+        out = head([f for f in host_feats], metas)          # plugin call, pinned host tensors in
+        return out["all_cls_scores"].cpu(), out["all_bbox_preds"].cpu()
+
+    def timed(fn, steps, warmup, collect=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        eng.sample_events = [] if collect else None
+        for _ in range(steps):
+            flush.fill_(1)                                   # evict L2 between timed steps (outside the events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        kern = eng.sample_events
+        eng.sample_events = None
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), kern
+
+    # valid (query, camera) pairs per layer -> algorithmic bytes of the sampling kernel
+    eng.keep_cam_masks, eng.cam_masks = True, []
+    step_resident()
+    torch.cuda.synchronize()
+    valid_pairs = [int(m.sum().item()) for m in eng.cam_masks]
+    eng.keep_cam_masks, eng.cam_masks = False, []
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    total_ms, kern = timed(step_resident, args.steps, max(args.warmup, 3), collect=True)
+    launches = (_lib.launch_count() - n0)
+    launches_per_step = launches // (args.steps + max(args.warmup, 3))
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms, _ = timed(step_e2e, e2e_steps, 2)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    e2e_value = world * B / (e2e_ms / e2e_steps * 1e-3)
+
+    # ---- roofline of the sampling kernel (HBM bound), measured live over the timed region
+    esz = 2 if args.precision == "bf16" else 4
+    C, Q, N, L = 256, 900, 6, 4
+    per_layer_bytes = [v * L * 4 * C * esz + B * Q * C * esz + B * Q * N * L * 4 + B * Q * 3 * 4 + B * N * 16 * 4
+                       for v in valid_pairs]
+    k_ms = [a.elapsed_time(b) for a, b in kern]
+    n_layers = len(valid_pairs)
+    per_layer_ms = [sum(k_ms[i::n_layers]) / max(1, len(k_ms[i::n_layers])) for i in range(n_layers)]
+    avg_ms = sum(k_ms) / len(k_ms)
+    avg_bytes = sum(per_layer_bytes) / n_layers
+    achieved = avg_bytes / (avg_ms * 1e-3) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    roofline = {"kernel": "sample_kernel (K1 fused camera sampling)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": avg_bytes, "avg_launch_ms": avg_ms,
+                "per_layer_ms": per_layer_ms, "valid_pairs_per_layer": valid_pairs,
+                "first_layer_gbs": per_layer_bytes[0] / (per_layer_ms[0] * 1e-3) / 1e9,
+                "note": "layer 1 of a step reads cold (L2 flushed); layers 2-6 re-touch mostly the same texels (L2 hits)",
+                "share_of_step": sum(k_ms) / total_ms}
+
+    h2d = sum(f.numel() * f.element_size() for f in host_feats) + B * N * 16 * 4 + B * 1500 * 36 * 4
+    d2h = 2 * 3 * B * Q * 10 * 4
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": workload_config(args),
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "note": "Detr3DHead.forward on pinned host feature maps; PCIe-bound by the feature hand-off that in "
+                            "deployment never leaves the GPU"},
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "clocks": sampler.summary()}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, args.cpu_samples)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+/*
+ * transcar_b200 - C ABI of the B200-native (sm_100a) TransCAR fusion-decoder hot path.
+ *
+ * Drop-in boundary.  The reference has no native code of its own on this path:
+ * its "FFI" is PyTorch's dispatcher reaching ATen/cuBLAS kernels from two Python files.  Each entry
+ * point below names the reference call site(s) it replaces; paths are relative to
+ * /root/reference/projects/mmdet3d_plugin/ with
+ *     T = models/utils/detr3d_transformer.py      H = models/dense_heads/detr3d_head.py
+ *     C = core/bbox/coders/nms_free_coder.py      U = core/bbox/util.py
+ *
+ * Conventions
+ *   - Plain C: POD structs of raw DEVICE pointers, int32 sizes, a CUDA stream handle.  No torch types.
+ *   - Ownership: the caller allocates every input, output and workspace; the library never allocates
+ *     or frees device memory and keeps no pointer after a call returns.
+ *   - Asynchronous: all work is enqueued on the caller's stream; no internal streams, no implicit sync.
+ *     Calls are capturable into CUDA graphs.
+ *   - Errors: 0 = ok, <0 = bad argument (TC_ERR_*), >0 = cudaError_t.  tc_last_error_string() describes
+ *     the last failure on the calling thread.  No C++ exception crosses the boundary.
+ *   - sm_100a only.  There is no CPU fallback and no other backend.
+ *   - Row-major everywhere.  "fp32"/"bf16" tensors are selected by tc_dtype fields.
+ */
+#ifndef TRANSCAR_B200_H_
+#define TRANSCAR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TC_API __attribute__((visibility("default")))
+#else
+#define TC_API
+#endif
+
+#define TC_ABI_VERSION 1
+#define TC_MAX_LEVELS 4
+#define TC_MAX_CAMS 8
+
+typedef void* tc_stream_t;                  /* cudaStream_t */
+
+typedef enum { TC_F32 = 0, TC_BF16 = 1 } tc_dtype;
+
+enum {
+  TC_OK = 0,
+  TC_ERR_NULL = -1,        /* required pointer is NULL */
+  TC_ERR_SHAPE = -2,       /* unsupported size */
+  TC_ERR_ALIGN = -3,       /* pointer / leading dimension not aligned as documented */
+  TC_ERR_DTYPE = -4,       /* unsupported dtype combination */
+  TC_ERR_DEVICE = -5       /* not an sm_100 device */
+};
+
+TC_API int tc_abi_version(void);
+TC_API const char* tc_last_error_string(void);
+/* 0 if the current CUDA device is compute capability 10.x, TC_ERR_DEVICE otherwise. */
+TC_API int tc_check_device(void);
+/* Number of kernels this library has enqueued from the calling process since load (bench evidence). */
+TC_API uint64_t tc_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  fused camera sampling.   Replaces T:381-422 (feature_sampling: projection through lidar2img,
+ * validity mask, 4x F.grid_sample bilinear/zeros/align_corners=False) and T:367-373 (NaN->0,
+ * sigmoid(attention_weights)*mask, sum over level/point/camera) in ONE kernel: one warp per query,
+ * cameras that fail the validity test are skipped, every texel is read with 128-bit loads from
+ * channels-last feature maps, result written once.
+ *
+ *   feat[l]      [B, N, H_l, W_l, C]  channels-last, feat_dtype (fp32 or bf16), 16-byte aligned, C % 256 == 0
+ *   ref          [B, Q, 3] fp32       normalised reference points in [0,1]
+ *   lidar2img    [B, N, 4, 4] fp32    (reference casts the float64 matrices to fp32 at T:386)
+ *   attn_logits  [B, Q, N*L] fp32     output of the attention_weights Linear, index = cam*L + level
+ *   out          [B, Q, C] out_dtype  sum_{cam,level} mask * sigmoid(logit) * bilinear(feat)
+ *   mask         [B, Q, N] uint8      optional (may be NULL): camera validity, bit-exact w.r.t. T:400-409
+ */
+typedef struct {
+  const void* feat[TC_MAX_LEVELS];
+  int32_t H[TC_MAX_LEVELS];
+  int32_t W[TC_MAX_LEVELS];
+  int32_t num_levels;
+  int32_t B, N, Q, C;
+  int32_t feat_dtype;
+  int32_t out_dtype;
+  const float* ref;
+  const float* lidar2img;
+  const float* attn_logits;
+  float pc_range[6];
+  float img_w, img_h;          /* img_metas[0]['img_shape'][0][1], [0][0] (quirk Q2) */
+  void* out;
+  uint8_t* mask;
+} tc_sample_args;
+TC_API int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream);
+
+/* NCHW fp32 -> channels-last (fp32 or bf16) layout conversion for callers whose backbone is not
+ * channels-last.  src [P, C, HW] fp32 -> dst [P, HW, C].  */
+TC_API int tc_nchw_to_nhwc(const float* src, void* dst, int32_t dst_dtype, int32_t planes, int32_t C, int32_t HW,
+                    tc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  Linear + fused epilogue.   Replaces every nn.Linear / LayerNorm / ReLU / residual chain on the path:
+ * mmcv FFN + norms (cfg detr3d_res101_gridmask.py:65-82), T:362,375,377 (attention_weights, output_proj,
+ * position_encoder), T:191 (reg_branches), H:533-536 (radar encoders), H:578 (q/k/v/out projections of
+ * nn.MultiheadAttention), H:583-586 (rf_norm2, rf_linear1/2, rf_norm3), H:592-593 (final_cls/final_reg).
+ *
+ *   Y = A[M,K] * W[N,K]^T                    (fp32 accumulate)
+ *   Y += bias[n]                              if bias
+ *   Y += row_bias[m % row_bias_period, n]     if row_bias     (e.g. the input-independent query_pos * W^T term)
+ *   Y  = row_gate[m] ? Y : 0                  if row_gate     (rows whose attention saw no key: quirk Q6)
+ *   Y += residual[m, n] (+ residual2[m, n])   if residual(2)
+ *   Y  = LayerNorm_N(Y) * gamma + beta        if ln_gamma     (eps = ln_eps, biased variance; needs N <= 512)
+ *   Y  = max(Y, 0)                            if relu
+ *   Y += post_add[m, n]                       if post_add     (H:536: pos_feat + ReLU(feat))
+ *   out_f32[m, n] = Y ; out_bf16[m, n] = bf16(Y)    (either may be NULL, not both)
+ *
+ * a_dtype/w_dtype: both TC_F32 -> exact-fp32 SIMT path (parity mode);  both TC_BF16 -> tcgen05 tensor-core
+ * path (K % 64 == 0, N % 16 == 0, 16-byte aligned rows) with SIMT fallback for the tiny odd shapes.
+ */
+typedef struct {
+  const void* A;  int32_t a_dtype;  int64_t lda;      /* elements */
+  const void* W;  int32_t w_dtype;  int64_t ldw;
+  int32_t M, N, K;
+  const float* bias;
+  const float* row_bias;  int32_t row_bias_period;  int64_t ld_row_bias;
+  const uint8_t* row_gate;
+  const float* residual;  int64_t ld_residual;
+  const float* residual2; int64_t ld_residual2;
+  const float* ln_gamma;  const float* ln_beta;  float ln_eps;
+  int32_t relu;
+  const float* post_add;  int64_t ld_post_add;
+  float* out_f32;  int64_t ld_out_f32;
+  void*  out_bf16; int64_t ld_out_bf16;
+} tc_linear_args;
+TC_API int tc_linear(const tc_linear_args* a, tc_stream_t stream);
+
+/* Fused 3 -> C position encoder head: Y = ReLU(LayerNorm(Linear_{3->C}(f(x)))), f = inverse_sigmoid (eps 1e-5,
+ * T:17-32) when logit_input != 0 else identity.  Replaces T:377 (position_encoder[0:3]) and H:533
+ * (radar_position_encoder[0:3]).  x is [M, ldx] fp32 (first 3 columns used); C <= 1024, C % 32 == 0. */
+typedef struct {
+  const float* x; int64_t ldx; int32_t M; int32_t C; int32_t logit_input;
+  const float* weight;   /* [C,3] */
+  const float* bias;     /* [C]   */
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
+  float* out_f32; void* out_bf16;   /* [M,C]; either may be NULL */
+} tc_point_embed_args;
+TC_API int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  multi-head attention core softmax(scale * Q K^T + mask) V on already-projected operands.
+ * Replaces the baddbmm -> softmax -> bmm core of nn.MultiheadAttention (slow path) for the
+ * decoder self-attention (mask-free) and for H:578 / H:649 / H:707 with the radar distance mask of
+ * H:549-571 built IN-KERNEL from per-query geometry (no [Q,R] mask tensor in HBM, no torch.where sync).
+ *
+ *   q [B, Lq, heads*D]  k, v [B, Lk, heads*D]   (dtype qkv_dtype; ld* = row stride in elements)
+ *   out [B, Lq, heads*D] out_dtype
+ *   geom (optional) [B, Lq, 8] fp32 = (cx, cy, fx, fy, rx, ry, radius, 0): centre / front / rear circle
+ *         centres in metres and the clamped radius - produced by tc_radar_geometry
+ *   key_xy (with geom) [B, Lk, 2] fp32 radar x,y in metres (padding slots hold 500)
+ *   row_any (optional) [B, Lq] uint8: 1 if the row has at least one allowed key.  Rows without any
+ *         allowed key produce out = 0 (they skip attention in the reference: quirk Q6).
+ */
+typedef struct {
+  const void* q; const void* k; const void* v;
+  int64_t ldq, ldk, ldv;
+  int64_t q_batch_stride, k_batch_stride, v_batch_stride;
+  int32_t qkv_dtype;
+  int32_t B, Lq, Lk, heads, D;
+  float scale;
+  const float* geom;
+  const float* key_xy;
+  void* out; int64_t ldo; int32_t out_dtype;
+  uint8_t* row_any;
+} tc_attention_args;
+TC_API int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream);
+
+/* Per-query circle geometry for the radar mask.  Replaces H:543-567 / H:615-635 / H:671-693.
+ *   centre [M, ld_centre] fp32: columns 0,1 = x,y.  centre_is_normalised != 0 -> x,y are in [0,1] and
+ *           are mapped to metres with pc_range first (layer 1: inter_references[-1]); else already metres.
+ *   code   [M, ld_code] fp32: previous stage regression; columns 3 (log length), 6, 7 (heading terms) used.
+ *   geom   [M, 8] fp32 out.   radius = clamp(exp(code[3]) / 2, r_lo, r_hi)  (quirk Q7). */
+typedef struct {
+  const float* centre; int64_t ld_centre; int32_t centre_is_normalised;
+  const float* code;   int64_t ld_code;
+  int32_t M;
+  float pc_range[6];
+  float r_lo, r_hi;
+  float* geom;
+} tc_radar_geometry_args;
+TC_API int tc_radar_geometry(const tc_radar_geometry_args* a, tc_stream_t stream);
+
+/* Materialise the [B, Lq, Lk] uint8 "blocked" mask (1 = key not attended) with exactly the arithmetic the
+ * attention kernel uses in-kernel: torch.cdist's mm-based Euclidean distance, '<' against the
+ * radius, OR of the three circles, NOT.  Test / debugging aid; the hot path never materialises it. */
+TC_API int tc_radar_mask(const float* geom, const float* key_xy, int32_t B, int32_t Lq, int32_t Lk,
+                  uint8_t* blocked, uint8_t* row_any, tc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small fused pointwise stages.
+ */
+/* Iterative reference refinement T:195-203:  new.xy = sigmoid(code.xy + logit(ref.xy)),
+ * new.z = sigmoid(code[4] + logit(ref.z)).   code [M, ld_code], ref/new_ref [M,3]. */
+TC_API int tc_ref_update(const float* code, int64_t ld_code, const float* ref, float* new_ref, int32_t M,
+                  tc_stream_t stream);
+
+/* Box-code assembly H:596-600 / H:664-665 / H:722-723:  code[0:2] += anchor_xy, code[4] += anchor_z, in place.
+ * anchor [M, ld_anchor]; xy_col/z_col select the columns; xy_from_normalised != 0 maps anchor x,y in [0,1]
+ * to metres with pc_range first while z is added as is (quirk Q3). */
+TC_API int tc_box_anchor_add(float* code, int64_t ld_code, const float* anchor, int64_t ld_anchor, int32_t xy_col,
+                      int32_t z_col, int32_t xy_from_normalised, const float* pc_range6, int32_t M,
+                      tc_stream_t stream);
+
+/* fp32 -> bf16 cast of a [rows, cols] matrix (weights are cast once, activations by fused epilogues). */
+TC_API int tc_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
+                 tc_stream_t stream);
+
+/* N1  NMS-free decode on device.  Replaces C:39-90 + U:26-52: sigmoid, top-`max_num` over Q*classes,
+ * denormalise (exp sizes, atan2 heading), centre-range test.  Fixed-size outputs, no host sync:
+ *   boxes [B, max_num, 9], scores [B, max_num], labels [B, max_num] int32, keep [B, max_num] uint8.
+ * workspace: tc_decode_workspace_bytes(B, Q, classes) bytes. */
+typedef struct {
+  const float* cls; const float* code;       /* [B,Q,classes], [B,Q,10] */
+  int32_t B, Q, classes, max_num;
+  float post_center_range[6];
+  float* boxes; float* scores; int32_t* labels; uint8_t* keep;
+  void* workspace;
+} tc_decode_args;
+TC_API int64_t tc_decode_workspace_bytes(int32_t B, int32_t Q, int32_t classes);
+TC_API int tc_decode(const tc_decode_args* a, tc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* TRANSCAR_B200_H_ */

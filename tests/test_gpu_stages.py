@@ -1,0 +1,396 @@
+"""Stage-level parity of every CUDA entry point against the oracle on identical inputs (``-m gpu``).
+
+All calls go through the C ABI (``transcar_b200.ops`` -> ctypes -> ``libtranscar_b200.so``).
+Tolerances (BASELINE.json north_star): masks bit-exact; fp32 values 1e-5; bf16 values 1e-3 abs + 1e-2 rel.
+The oracle runs twice where arithmetic order matters: on the GPU (same ATen kernels the reference would
+use in deployment) and on the CPU (the committed golden vectors come from there).
+"""
+import math
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fusion_decoder as O
+from transcar_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+BF16_ATOL, BF16_RTOL = 1e-3, 1e-2
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from transcar_b200 import _lib, ops as _ops
+    lib = _lib.load()
+    assert lib.tc_check_device() == 0, lib.tc_last_error_string()
+    return _ops
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev())
+
+
+# ------------------------------------------------------------------------------------------- K1
+def _sampling_case(B, Q, config, seed, smooth):
+    feats = synthetic.make_feats(seed, B, config, smooth=smooth)
+    metas = synthetic.make_img_metas(B, seed=seed)
+    g = torch.Generator().manual_seed(seed + 11)
+    ref = torch.rand((B, Q, 3), generator=g)
+    ref[:, : Q // 8] = ref[:, : Q // 8] * 1.2 - 0.1          # some points outside [0,1] / behind cameras
+    logits = torch.randn((B, Q, 24), generator=g)
+    return feats, metas, ref, logits
+
+
+def _oracle_sampled_sum(feats, metas, ref, logits, device):
+    """T:365-373 with explicit attention logits (the Linear is tested separately)."""
+    feats = [f.to(device) for f in feats]
+    ref, logits = ref.to(device), logits.to(device)
+    B, Q, _ = ref.shape
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, sampled, mask = O.feature_sampling(feats, ref, metas)
+    sampled = torch.nan_to_num(sampled, nan=0.0)
+    w = logits.view(B, 1, Q, 6, 1, 4).sigmoid() * mask
+    out = (sampled * w).sum(-1).sum(-1).sum(-1).permute(0, 2, 1)
+    return out, mask[:, 0, :, :, 0, 0]
+
+
+@pytest.mark.parametrize("config,B,Q", [("tiny", 2, 300), ("res101", 1, 900)])
+def test_sample_fp32_vs_oracle(ops, config, B, Q):
+    feats, metas, ref, logits = _sampling_case(B, Q, config, seed=5, smooth=False)
+    l2i = torch.tensor(np.asarray([m["lidar2img"] for m in metas]), dtype=torch.float32, device=dev())
+    cl = [ops.to_channels_last(f.to(dev())) for f in feats]
+    out, mask = ops.sample_fwd(cl, ref.to(dev()), l2i, logits.to(dev()), synthetic.PC_RANGE, 1600, 928, want_mask=True)
+    torch.cuda.synchronize()
+    # (1) oracle on the GPU: the arithmetic the reference has in deployment
+    want_g, mask_g = _oracle_sampled_sum(feats, metas, ref, logits, dev())
+    assert torch.equal(mask.bool(), mask_g), "camera validity mask must be bit-exact (GPU oracle)"
+    assert mask.sum().item() > 0
+    torch.testing.assert_close(out, want_g, rtol=0, atol=1e-5)
+    # (2) oracle on the CPU: ATen's CPU grid_sample un-normalises coordinates with a different rounding
+    # (SURVEY H2), so white-noise texels allow 1e-4 here; mask still bit-exact
+    want_c, mask_c = _oracle_sampled_sum(feats, metas, ref, logits, "cpu")
+    assert torch.equal(mask.bool().cpu(), mask_c), "camera validity mask must be bit-exact (CPU oracle)"
+    torch.testing.assert_close(out.cpu(), want_c, rtol=0, atol=1e-4)
+
+
+def test_sample_smooth_feats_1e5_vs_cpu_oracle(ops):
+    feats, metas, ref, logits = _sampling_case(2, 256, "tiny", seed=9, smooth=True)
+    l2i = torch.tensor(np.asarray([m["lidar2img"] for m in metas]), dtype=torch.float32, device=dev())
+    cl = [ops.to_channels_last(f.to(dev())) for f in feats]
+    out, _ = ops.sample_fwd(cl, ref.to(dev()), l2i, logits.to(dev()), synthetic.PC_RANGE, 1600, 928)
+    want_c, _ = _oracle_sampled_sum(feats, metas, ref, logits, "cpu")
+    torch.testing.assert_close(out.cpu(), want_c, rtol=0, atol=1e-5)
+
+
+def test_sample_bf16_and_layouts(ops):
+    feats, metas, ref, logits = _sampling_case(2, 300, "tiny", seed=6, smooth=False)
+    l2i = torch.tensor(np.asarray([m["lidar2img"] for m in metas]), dtype=torch.float32, device=dev())
+    f16 = [f.to(dev()).to(torch.bfloat16) for f in feats]
+    cl16 = [f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3) for f in f16]       # zero-copy layout
+    out16, mask16 = ops.sample_fwd(cl16, ref.to(dev()), l2i, logits.to(dev()), synthetic.PC_RANGE, 1600, 928,
+                                   out_dtype=torch.bfloat16, want_mask=True)
+    # reference on the SAME bf16-rounded texels in fp32 arithmetic
+    want, mask = _oracle_sampled_sum([f.float() for f in f16], metas, ref, logits, dev())
+    assert torch.equal(mask16.bool(), mask)
+    torch.testing.assert_close(out16.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL)
+    # fp32 output from bf16 features is exact up to accumulation order
+    out32, _ = ops.sample_fwd(cl16, ref.to(dev()), l2i, logits.to(dev()), synthetic.PC_RANGE, 1600, 928)
+    torch.testing.assert_close(out32, want, rtol=0, atol=2e-5)
+    # NCHW fp32 hand-off goes through tc_nchw_to_nhwc (also to bf16)
+    conv = ops.to_channels_last(feats[0].to(dev()), torch.bfloat16)
+    assert torch.equal(conv, feats[0].to(dev()).to(torch.bfloat16))
+    assert ops.is_channels_last_5d(conv)
+
+
+def test_sample_edge_cases(ops):
+    feats, metas, _, _ = _sampling_case(1, 8, "tiny", seed=2, smooth=False)
+    l2i = torch.tensor(np.asarray([m["lidar2img"] for m in metas]), dtype=torch.float32, device=dev())
+    cl = [ops.to_channels_last(f.to(dev())) for f in feats]
+    # empty query set
+    out, mask = ops.sample_fwd(cl, torch.zeros((1, 0, 3), device=dev()), l2i, torch.zeros((1, 0, 24), device=dev()),
+                               synthetic.PC_RANGE, 1600, 928, want_mask=True)
+    assert out.shape == (1, 0, 256) and mask.shape == (1, 0, 6)
+    # points that no camera sees -> exact zeros, all-false mask (NaN/inf-free: z clamped at 1e-5)
+    ref = torch.tensor([[[0.5, 0.5, 40.0], [0.5, 0.5, -40.0], [1e9, 0.0, 0.5], [float("nan"), 0.5, 0.5]]], device=dev())
+    out, mask = ops.sample_fwd(cl, ref, l2i, torch.zeros((1, 4, 24), device=dev()), synthetic.PC_RANGE, 1600, 928,
+                               want_mask=True)
+    want, mask_o = _oracle_sampled_sum(feats, metas, ref.cpu(), torch.zeros((1, 4, 24)), dev())
+    assert torch.equal(mask.bool(), mask_o)
+    assert torch.isfinite(out).all()
+    torch.testing.assert_close(out, want, rtol=0, atol=1e-5)
+    # non channels-last input is refused loudly
+    with pytest.raises(RuntimeError):
+        ops.sample_fwd([f.to(dev()) for f in feats], ref, l2i, torch.zeros((1, 4, 24), device=dev()),
+                       synthetic.PC_RANGE, 1600, 928)
+
+
+# ------------------------------------------------------------------------------------------- K3
+def _ref_linear(A, W, bias=None, row_bias=None, period=0, gate=None, res=None, res2=None, ln=None, relu=False,
+                post=None):
+    y = A.double() @ W.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if row_bias is not None:
+        idx = torch.arange(A.shape[0], device=A.device) % period
+        y = y + row_bias.double()[idx]
+    if gate is not None:
+        y = y * gate.double().unsqueeze(1)
+    if res is not None:
+        y = y + res.double()
+    if res2 is not None:
+        y = y + res2.double()
+    if ln is not None:
+        y = F.layer_norm(y, (y.shape[1],), ln[0].double(), ln[1].double(), 1e-5)
+    if relu:
+        y = y.relu()
+    if post is not None:
+        y = y + post.double()
+    return y.float()
+
+
+@pytest.mark.parametrize("M,N,K", [(900, 256, 256), (77, 512, 256), (1500, 64, 36), (333, 10, 256), (900, 24, 256),
+                                   (64, 768, 256), (1, 256, 512), (130, 128, 64)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_linear_plain(ops, M, N, K, mode):
+    A, W, b = rnd((M, K), 1), rnd((N, K), 2, K ** -0.5), rnd((N,), 3, 0.1)
+    if mode == "bf16":
+        A16, W16 = A.bfloat16(), W.bfloat16()
+        o32, o16 = ops.linear(A16, W16, b, relu=True, want_f32=True, want_bf16=True)
+        want = _ref_linear(A16.float(), W16.float(), b, relu=True)
+        torch.testing.assert_close(o32, want, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(o16.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL)
+    else:
+        o32, _ = ops.linear(A, W, b, relu=True)
+        torch.testing.assert_close(o32, _ref_linear(A, W, b, relu=True), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_linear_full_epilogue(ops, mode):
+    M, N, K, period = 1800, 256, 512, 900
+    A, W, b = rnd((M, K), 4), rnd((N, K), 5, K ** -0.5), rnd((N,), 6, 0.1)
+    rb, res, res2, post = rnd((period, N), 7, 0.3), rnd((M, N), 8), rnd((M, N), 9), rnd((M, N), 10)
+    gate = (torch.arange(M, device=dev()) % 3 != 0).to(torch.uint8)
+    ln = (1 + 0.1 * rnd((N,), 11), 0.1 * rnd((N,), 12))
+    kw = dict(row_bias=rb, row_bias_period=period, row_gate=gate, residual=res, residual2=res2, ln=ln, relu=True,
+              post_add=post)
+    if mode == "bf16":
+        A, W = A.bfloat16(), W.bfloat16()
+    o32, o16 = ops.linear(A, W, b, want_f32=True, want_bf16=True, **kw)
+    want = _ref_linear(A.float(), W.float(), b, rb, period, gate, res, res2, ln, True, post)
+    tol = dict(rtol=1e-5, atol=2e-5) if mode == "fp32" else dict(rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(o32, want, **tol)
+    torch.testing.assert_close(o16.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL * 4)
+    # strided output / operand views (qkv slices, stacked outputs)
+    big = torch.zeros((M, 3 * N), device=dev())
+    ops.linear(A, W, b, out_f32=big[:, N:2 * N])
+    torch.testing.assert_close(big[:, N:2 * N], _ref_linear(A.float(), W.float(), b), rtol=1e-4, atol=1e-4)
+    assert big[:, :N].abs().sum() == 0 and big[:, 2 * N:].abs().sum() == 0
+
+
+def test_linear_matches_oracle_ffn_block(ops):
+    """FFN + norm of a decoder layer, oracle weights (fp32 path, 1e-5)."""
+    sd = {k: v.to(dev()) for k, v in synthetic.make_state_dict(1, 128).items()}
+    p = "transformer.decoder.layers.2"
+    x = rnd((640, 256), 21)
+    h, _ = ops.linear(x, sd[p + ".ffns.0.layers.0.0.weight"], sd[p + ".ffns.0.layers.0.0.bias"], relu=True)
+    y, _ = ops.linear(h, sd[p + ".ffns.0.layers.1.weight"], sd[p + ".ffns.0.layers.1.bias"], residual=x,
+                      ln=(sd[p + ".norms.2.weight"], sd[p + ".norms.2.bias"]))
+    hh = F.relu(O.lin(sd, p + ".ffns.0.layers.0.0", x))
+    want = O.lnorm(sd, p + ".norms.2", x + O.lin(sd, p + ".ffns.0.layers.1", hh))
+    torch.testing.assert_close(y, want, rtol=1e-5, atol=1e-5)
+
+
+def test_linear_bad_arguments(ops):
+    A, W = rnd((4, 8), 1), rnd((3, 8), 2)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.linear(A.cpu(), W)
+    with pytest.raises(RuntimeError, match="LayerNorm needs N"):
+        ops.linear(rnd((4, 8), 1), rnd((300, 8), 2), ln=(rnd((300,), 3), rnd((300,), 4)))
+    o, _ = ops.linear(torch.zeros((0, 8), device=dev()), W)        # empty M is fine
+    assert o.shape == (0, 3)
+
+
+def test_point_embed(ops):
+    sd = {k: v.to(dev()) for k, v in synthetic.make_state_dict(1, 128).items()}
+    p = "transformer.decoder.layers.1.attentions.1.position_encoder"
+    g = torch.Generator().manual_seed(3)
+    ref = torch.rand((1000, 3), generator=g).to(dev())
+    ref[:5] = torch.tensor([0.0, 1.0, 1e-7, 0.5, 1 - 1e-7], device=dev()).unsqueeze(1)
+    o32, o16 = ops.point_embed(ref, sd[p + ".0.weight"], sd[p + ".0.bias"], sd[p + ".1.weight"], sd[p + ".1.bias"],
+                               logit_input=True, want_bf16=True)
+    want = F.relu(O.lnorm(sd, p + ".1", O.lin(sd, p + ".0", O.logit(ref))))
+    torch.testing.assert_close(o32, want, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(o16.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL)
+    # radar variant: raw xyz columns of a [M,36] token matrix, including the 500 padding rows
+    tok = rnd((700, 36), 5, 20.0)
+    tok[600:] = 500.0
+    q = "radar_position_encoder"
+    o32, _ = ops.point_embed(tok, sd[q + ".0.weight"], sd[q + ".0.bias"], sd[q + ".1.weight"], sd[q + ".1.bias"],
+                             logit_input=False)
+    want = F.relu(O.lnorm(sd, q + ".1", O.lin(sd, q + ".0", tok[:, :3])))
+    torch.testing.assert_close(o32, want, rtol=1e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------- K4 + mask
+def _geometry_inputs(B, Q, R, seed):
+    g = torch.Generator().manual_seed(seed)
+    radar_xy = (torch.rand((B, R, 2), generator=g) * 102.4 - 51.2)
+    radar_xy[:, R - R // 5:] = 500.0                                   # padding slots (quirk Q5)
+    centre = torch.rand((B, Q, 3), generator=g)                          # normalised
+    code = torch.randn((B, Q, 10), generator=g) * 0.3
+    code[..., 3] += 1.0
+    return radar_xy.to(dev()), centre.to(dev()), code.to(dev())
+
+
+def _oracle_blocked(centre_m, code, radar_xy, lo, hi):
+    out = []
+    for b in range(centre_m.shape[0]):
+        out.append(O.radar_block_mask(centre_m[b:b + 1, :, :2].clone(), code[b:b + 1, :, 3].exp(), -code[b:b + 1, :, 6],
+                                      -code[b:b + 1, :, 7], radar_xy[b:b + 1], lo, hi))
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize("lo,hi,normalised", [(1.0, 2.0, True), (0.5, 1.0, False)])
+def test_radar_mask_bit_exact(ops, lo, hi, normalised):
+    B, Q, R = 2, 900, 1500
+    radar_xy, centre, code = _geometry_inputs(B, Q, R, seed=17)
+    centre_m = O.to_metres(centre)
+    src = centre if normalised else centre_m
+    geom = ops.radar_geometry(src.view(B * Q, 3), code.view(B * Q, 10), synthetic.PC_RANGE, lo, hi, normalised)
+    blocked, row_any = ops.radar_mask(geom, radar_xy, B, Q, R)
+    want_gpu = _oracle_blocked(centre_m, code, radar_xy, lo, hi)                       # torch.cdist on the GPU
+    want_cpu = _oracle_blocked(centre_m.cpu(), code.cpu(), radar_xy.cpu(), lo, hi)     # and on the CPU
+    n_allowed = int((~want_gpu).sum())
+    assert n_allowed > 100
+    assert torch.equal(blocked.bool(), want_gpu), \
+        f"radar mask differs from torch.cdist(GPU) in {(blocked.bool() != want_gpu).sum().item()} of {want_gpu.numel()} bits"
+    assert torch.equal(blocked.bool().cpu(), want_cpu), \
+        f"radar mask differs from torch.cdist(CPU) in {(blocked.bool().cpu() != want_cpu).sum().item()} bits"
+    assert torch.equal(row_any.bool(), (~want_gpu).any(-1))
+
+
+def _oracle_mha_core(q, k, v, heads, blocked=None):
+    """softmax(q k^T / sqrt(d) + mask) v per head, fp64; rows with no allowed key -> 0."""
+    B, Lq, E = q.shape
+    D = E // heads
+    qh = q.double().view(B, Lq, heads, D).transpose(1, 2)
+    kh = k.double().view(B, -1, heads, D).transpose(1, 2)
+    vh = v.double().view(B, -1, heads, D).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(D)
+    if blocked is not None:
+        s = s.masked_fill(blocked.unsqueeze(1), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = torch.nan_to_num(p, nan=0.0)
+    return (p @ vh).transpose(1, 2).reshape(B, Lq, E).float()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("Lq,Lk", [(900, 900), (130, 77), (1, 1500)])
+def test_attention_dense(ops, mode, Lq, Lk):
+    B, heads, E = 2, 8, 256
+    q, k, v = rnd((B, Lq, E), 1), rnd((B, Lk, E), 2), rnd((B, Lk, E), 3)
+    if mode == "bf16":
+        q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    out, _ = ops.attention(q, k, v, heads)
+    want = _oracle_mha_core(q.float(), k.float(), v.float(), heads)
+    if mode == "fp32":
+        torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+    else:
+        torch.testing.assert_close(out.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_attention_radar_mask_in_kernel(ops, mode):
+    B, Q, R, heads, E = 2, 900, 1500, 8, 256
+    radar_xy, centre, code = _geometry_inputs(B, Q, R, seed=23)
+    geom = ops.radar_geometry(centre.view(B * Q, 3), code.view(B * Q, 10), synthetic.PC_RANGE, 1.0, 2.0, True)
+    blocked = _oracle_blocked(O.to_metres(centre), code, radar_xy, 1.0, 2.0)
+    # qkv as strided views of one packed buffer (how the engine hands them over)
+    qbuf, kvbuf = rnd((B, Q, E), 4), rnd((B, R, 2 * E), 5)
+    if mode == "bf16":
+        qbuf, kvbuf = qbuf.bfloat16(), kvbuf.bfloat16()
+    out, row_any = ops.attention(qbuf, kvbuf[:, :, :E], kvbuf[:, :, E:], heads, geom=geom, key_xy=radar_xy,
+                                 want_row_any=True)
+    want = _oracle_mha_core(qbuf.float(), kvbuf[:, :, :E].float(), kvbuf[:, :, E:].float(), heads, blocked)
+    any_allowed = (~blocked).any(-1)
+    assert torch.equal(row_any.bool(), any_allowed)
+    assert 0 < any_allowed.sum() < B * Q
+    assert (out[~any_allowed] == 0).all(), "rows without an allowed key must produce exact zeros (quirk Q6)"
+    if mode == "fp32":
+        torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+    else:
+        torch.testing.assert_close(out.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
+
+
+def test_attention_matches_nn_multiheadattention(ops):
+    """Whole nn.MultiheadAttention (in-proj, core, out-proj) with a bool mask == the oracle's mha(), fp32."""
+    sd = {k: v.to(dev()) for k, v in synthetic.make_state_dict(1, 128).items()}
+    B, Q, R, E = 1, 300, 500, 256
+    radar_xy, centre, code = _geometry_inputs(B, Q, R, seed=29)
+    blocked = _oracle_blocked(O.to_metres(centre), code, radar_xy, 1.0, 2.0)[0]
+    rows = torch.where((~blocked).any(1))[0]
+    x, kv = rnd((Q, 1, E), 6), rnd((R, 1, E), 7)
+    want = O.mha(sd, "rf_multihead_attn", x[rows], kv, kv, attn_mask=blocked[rows])
+    w, b = sd["rf_multihead_attn.in_proj_weight"], sd["rf_multihead_attn.in_proj_bias"]
+    qp, _ = ops.linear(x[:, 0], w[:E], b[:E])
+    kvp, _ = ops.linear(kv[:, 0], w[E:], b[E:])
+    geom = ops.radar_geometry(centre.view(Q, 3), code.view(Q, 10), synthetic.PC_RANGE, 1.0, 2.0, True)
+    att, row_any = ops.attention(qp.view(1, Q, E), kvp.view(1, R, 2 * E)[:, :, :E], kvp.view(1, R, 2 * E)[:, :, E:], 8,
+                                 geom=geom, key_xy=radar_xy, want_row_any=True)
+    y, _ = ops.linear(att.view(Q, E), sd["rf_multihead_attn.out_proj.weight"], sd["rf_multihead_attn.out_proj.bias"],
+                      row_gate=row_any.view(Q))
+    torch.testing.assert_close(y[rows], want[:, 0], rtol=1e-5, atol=1e-5)
+    mask = torch.ones(Q, dtype=torch.bool, device=dev())
+    mask[rows] = False
+    assert (y[mask] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------- pointwise + decode
+def test_ref_update_and_anchor(ops):
+    g = torch.Generator().manual_seed(31)
+    ref = torch.rand((1200, 3), generator=g).to(dev())
+    ref[:4, 0] = torch.tensor([0.0, 1.0, 1e-6, 1 - 1e-6], device=dev())
+    code = rnd((1200, 10), 32)
+    new = ops.ref_update(code, ref)
+    want = torch.zeros_like(ref)
+    want[..., :2] = code[..., :2] + O.logit(ref[..., :2])
+    want[..., 2:3] = code[..., 4:5] + O.logit(ref[..., 2:3])
+    torch.testing.assert_close(new, want.sigmoid(), rtol=1e-6, atol=1e-6)
+    # layer 1 anchor: normalised ref -> metres for x,y; z added as is (quirk Q3)
+    reg = rnd((1200, 10), 33)
+    want = reg.clone()
+    m = O.to_metres(ref)
+    want[:, 0:2] += m[:, 0:2]
+    want[:, 4] += ref[:, 2]
+    got = ops.box_anchor_add(reg.clone(), ref, 0, 2, True, synthetic.PC_RANGE)
+    assert torch.equal(got, want)
+    # later layers: previous code columns 0,1,4
+    prev = rnd((1200, 10), 34, 10.0)
+    want = reg.clone()
+    want[:, 0:2] += prev[:, 0:2]
+    want[:, 4] += prev[:, 4]
+    assert torch.equal(ops.box_anchor_add(reg.clone(), prev, 0, 4, False, synthetic.PC_RANGE), want)
+
+
+def test_decode_vs_oracle(ops):
+    B, Q = 3, 900
+    cls, code = rnd((B, Q, 10), 41, 2.0), rnd((B, Q, 10), 42)
+    code[..., 0:2] *= 40.0          # some centres outside the +-61.2 post range
+    rng = [-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]
+    boxes, scores, labels, keep = ops.decode(cls, code, 300, rng)
+    for b in range(B):
+        want = O.nms_free_decode(cls[b], code[b], 300, 10, rng)
+        k = keep[b].bool()
+        assert 0 < k.sum() < 300
+        torch.testing.assert_close(scores[b][k], want["scores"], rtol=0, atol=1e-6)
+        assert torch.equal(labels[b][k].long(), want["labels"])
+        torch.testing.assert_close(boxes[b][k], want["bboxes"], rtol=1e-6, atol=1e-5)

@@ -1,0 +1,131 @@
+"""ctypes binding of ``libtranscar_b200.so`` (the C ABI declared in ``include/transcar_b200.h``).
+
+There is no fallback: if the shared library is missing this module raises at first use with the
+build command, and every call raises ``RuntimeError`` carrying ``tc_last_error_string()`` on a
+non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtranscar_b200.so")
+
+TC_F32, TC_BF16 = 0, 1
+TC_MAX_LEVELS, TC_MAX_CAMS = 4, 8
+ABI_VERSION = 1
+
+_vp, _i32, _i64, _f32, _u8p = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [("feat", _vp * TC_MAX_LEVELS), ("H", _i32 * TC_MAX_LEVELS), ("W", _i32 * TC_MAX_LEVELS),
+                ("num_levels", _i32), ("B", _i32), ("N", _i32), ("Q", _i32), ("C", _i32),
+                ("feat_dtype", _i32), ("out_dtype", _i32),
+                ("ref", _vp), ("lidar2img", _vp), ("attn_logits", _vp),
+                ("pc_range", _f32 * 6), ("img_w", _f32), ("img_h", _f32),
+                ("out", _vp), ("mask", _vp)]
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [("A", _vp), ("a_dtype", _i32), ("lda", _i64),
+                ("W", _vp), ("w_dtype", _i32), ("ldw", _i64),
+                ("M", _i32), ("N", _i32), ("K", _i32),
+                ("bias", _vp),
+                ("row_bias", _vp), ("row_bias_period", _i32), ("ld_row_bias", _i64),
+                ("row_gate", _vp),
+                ("residual", _vp), ("ld_residual", _i64),
+                ("residual2", _vp), ("ld_residual2", _i64),
+                ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_eps", _f32),
+                ("relu", _i32),
+                ("post_add", _vp), ("ld_post_add", _i64),
+                ("out_f32", _vp), ("ld_out_f32", _i64),
+                ("out_bf16", _vp), ("ld_out_bf16", _i64)]
+
+
+class PointEmbedArgs(C.Structure):
+    _fields_ = [("x", _vp), ("ldx", _i64), ("M", _i32), ("C", _i32), ("logit_input", _i32),
+                ("weight", _vp), ("bias", _vp), ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_eps", _f32),
+                ("out_f32", _vp), ("out_bf16", _vp)]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [("q", _vp), ("k", _vp), ("v", _vp),
+                ("ldq", _i64), ("ldk", _i64), ("ldv", _i64),
+                ("q_batch_stride", _i64), ("k_batch_stride", _i64), ("v_batch_stride", _i64),
+                ("qkv_dtype", _i32),
+                ("B", _i32), ("Lq", _i32), ("Lk", _i32), ("heads", _i32), ("D", _i32),
+                ("scale", _f32),
+                ("geom", _vp), ("key_xy", _vp),
+                ("out", _vp), ("ldo", _i64), ("out_dtype", _i32),
+                ("row_any", _vp)]
+
+
+class RadarGeometryArgs(C.Structure):
+    _fields_ = [("centre", _vp), ("ld_centre", _i64), ("centre_is_normalised", _i32),
+                ("code", _vp), ("ld_code", _i64),
+                ("M", _i32),
+                ("pc_range", _f32 * 6), ("r_lo", _f32), ("r_hi", _f32),
+                ("geom", _vp)]
+
+
+class DecodeArgs(C.Structure):
+    _fields_ = [("cls", _vp), ("code", _vp),
+                ("B", _i32), ("Q", _i32), ("classes", _i32), ("max_num", _i32),
+                ("post_center_range", _f32 * 6),
+                ("boxes", _vp), ("scores", _vp), ("labels", _vp), ("keep", _vp),
+                ("workspace", _vp)]
+
+
+# every symbol include/transcar_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "tc_abi_version": (C.c_int, []),
+    "tc_last_error_string": (C.c_char_p, []),
+    "tc_check_device": (C.c_int, []),
+    "tc_launch_count": (C.c_uint64, []),
+    "tc_sample_fwd": (C.c_int, [C.POINTER(SampleArgs), _vp]),
+    "tc_nchw_to_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tc_linear": (C.c_int, [C.POINTER(LinearArgs), _vp]),
+    "tc_point_embed": (C.c_int, [C.POINTER(PointEmbedArgs), _vp]),
+    "tc_attention_fwd": (C.c_int, [C.POINTER(AttentionArgs), _vp]),
+    "tc_radar_geometry": (C.c_int, [C.POINTER(RadarGeometryArgs), _vp]),
+    "tc_radar_mask": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "tc_ref_update": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp]),
+    "tc_box_anchor_add": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, C.POINTER(_f32 * 6), _i32, _vp]),
+    "tc_cast_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "tc_decode_workspace_bytes": (C.c_int64, [_i32, _i32, _i32]),
+    "tc_decode": (C.c_int, [C.POINTER(DecodeArgs), _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise (never fall back) when it is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"transcar_b200: CUDA library {LIB_PATH} is missing and there is no CPU fallback. "
+            f"Build it with `python -m transcar_b200.build` (nvcc, sm_100a).")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)       # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.tc_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"transcar_b200: ABI version mismatch (library {lib.tc_abi_version()}, binding {ABI_VERSION})")
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().tc_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"transcar_b200.{what} failed with code {code}: {msg}")
+
+
+def launch_count():
+    return int(load().tc_launch_count())

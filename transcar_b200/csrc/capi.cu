@@ -1,0 +1,102 @@
+// C-ABI plumbing: error state, launch accounting, argument validation and path dispatch for
+// tc_linear / tc_attention_fwd.  See include/transcar_b200.h.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "tc_common.cuh"
+
+namespace tc {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return TC_OK;
+}
+
+int linear_simt_launch(const tc_linear_args* a, cudaStream_t s);
+int attention_simt_launch(const tc_attention_args* a, cudaStream_t s);
+bool linear_tc_supported(const tc_linear_args* a);
+int linear_tc_launch(const tc_linear_args* a, cudaStream_t s);
+bool attention_tc_supported(const tc_attention_args* a);
+int attention_tc_launch(const tc_attention_args* a, cudaStream_t s);
+
+}  // namespace tc
+
+extern "C" int tc_abi_version(void) { return TC_ABI_VERSION; }
+extern "C" const char* tc_last_error_string(void) { return tc::g_err; }
+extern "C" uint64_t tc_launch_count(void) { return tc::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int tc_check_device(void) {
+  int dev = 0, major = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) {
+    tc::set_error("tc_check_device: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  if (major != 10) {
+    tc::set_error("tc_check_device: compute capability %d.x is not sm_100 (this library is B200-only)", major);
+    return TC_ERR_DEVICE;
+  }
+  return TC_OK;
+}
+
+extern "C" int tc_linear(const tc_linear_args* a, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_linear: args is NULL");
+  TC_REQUIRE(a->A && a->W, TC_ERR_NULL, "tc_linear: A or W is NULL");
+  TC_REQUIRE(a->out_f32 || a->out_bf16, TC_ERR_NULL, "tc_linear: no output pointer");
+  TC_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, TC_ERR_SHAPE, "tc_linear: bad M/N/K %d/%d/%d", a->M, a->N, a->K);
+  TC_REQUIRE(a->lda >= a->K && a->ldw >= a->K, TC_ERR_SHAPE, "tc_linear: leading dimension smaller than K");
+  TC_REQUIRE((a->a_dtype == TC_F32 || a->a_dtype == TC_BF16) && (a->w_dtype == TC_F32 || a->w_dtype == TC_BF16),
+             TC_ERR_DTYPE, "tc_linear: bad dtype");
+  TC_REQUIRE(!a->ln_gamma || a->ln_beta, TC_ERR_NULL, "tc_linear: ln_gamma without ln_beta");
+  TC_REQUIRE(!a->ln_gamma || a->N <= 256, TC_ERR_SHAPE, "tc_linear: fused LayerNorm needs N <= 256 (got %d)", a->N);
+  TC_REQUIRE(!a->row_bias || a->row_bias_period > 0, TC_ERR_SHAPE, "tc_linear: row_bias needs a positive period");
+  TC_REQUIRE(!a->out_f32 || a->ld_out_f32 >= a->N, TC_ERR_SHAPE, "tc_linear: ld_out_f32 < N");
+  TC_REQUIRE(!a->out_bf16 || a->ld_out_bf16 >= a->N, TC_ERR_SHAPE, "tc_linear: ld_out_bf16 < N");
+  if (a->M == 0) return TC_OK;
+  cudaStream_t s = as_stream(stream);
+  if (linear_tc_supported(a)) return linear_tc_launch(a, s);
+  return linear_simt_launch(a, s);
+}
+
+extern "C" int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_attention_fwd: args is NULL");
+  TC_REQUIRE(a->q && a->k && a->v && a->out, TC_ERR_NULL, "tc_attention_fwd: NULL tensor pointer");
+  TC_REQUIRE(a->D == 32, TC_ERR_SHAPE, "tc_attention_fwd: head dim must be 32 (got %d)", a->D);
+  TC_REQUIRE(a->B >= 0 && a->Lq >= 0 && a->Lk >= 0 && a->heads > 0 && a->B <= 65535 && a->heads <= 65535,
+             TC_ERR_SHAPE, "tc_attention_fwd: bad shape");
+  TC_REQUIRE(a->qkv_dtype == TC_F32 || a->qkv_dtype == TC_BF16, TC_ERR_DTYPE, "tc_attention_fwd: bad qkv dtype");
+  TC_REQUIRE(a->out_dtype == TC_F32 || a->out_dtype == TC_BF16, TC_ERR_DTYPE, "tc_attention_fwd: bad out dtype");
+  TC_REQUIRE((a->geom == nullptr) == (a->key_xy == nullptr), TC_ERR_NULL,
+             "tc_attention_fwd: geom and key_xy must be given together");
+  const int64_t hd = (int64_t)a->heads * a->D;
+  TC_REQUIRE(a->ldq >= hd && a->ldk >= hd && a->ldv >= hd && a->ldo >= hd, TC_ERR_SHAPE,
+             "tc_attention_fwd: leading dimension smaller than heads*D");
+  const int es = a->qkv_dtype == TC_BF16 ? 2 : 4, eo = a->out_dtype == TC_BF16 ? 2 : 4;
+  TC_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->out) &&
+                 (a->ldq * es) % 16 == 0 && (a->ldk * es) % 16 == 0 && (a->ldv * es) % 16 == 0 &&
+                 (a->ldo * eo) % 16 == 0 && (a->q_batch_stride * es) % 16 == 0 && (a->k_batch_stride * es) % 16 == 0 &&
+                 (a->v_batch_stride * es) % 16 == 0,
+             TC_ERR_ALIGN, "tc_attention_fwd: q/k/v/out rows must be 16-byte aligned");
+  if (a->B == 0 || a->Lq == 0) return TC_OK;
+  cudaStream_t s = as_stream(stream);
+  if (attention_tc_supported(a)) return attention_tc_launch(a, s);
+  return attention_simt_launch(a, s);
+}

@@ -1,0 +1,250 @@
+// K3 (exact path): Linear + fused epilogue on the CUDA cores, fp32 FFMA accumulation.
+// This is the parity mode (fp32 operands, 1e-5 vs the reference) and the fallback for the tiny odd
+// shapes of the bf16 build (N = 10, 24; K = 36).  The tensor-core (tcgen05) path lives in linear_tc.cu.
+//
+// Tile: 32 rows x 256 columns per 256-thread block, K step 16.  Thread (warp w, lane l) owns rows
+// 4w..4w+3 and columns 8l..8l+7, so a full output row lives in one warp and the LayerNorm epilogue is a
+// pair of warp reductions - no second pass over HBM.
+#include "tc_common.cuh"
+
+namespace tc {
+namespace {
+
+constexpr int BM = 32, BN = 256, BK = 16;
+
+struct LinearParams {
+  const void* A; long long lda;
+  const void* W; long long ldw;
+  int M, N, K;
+  const float* bias;
+  const float* row_bias; int row_bias_period; long long ld_row_bias;
+  const uint8_t* row_gate;
+  const float* residual; long long ld_residual;
+  const float* residual2; long long ld_residual2;
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
+  int relu;
+  const float* post_add; long long ld_post_add;
+  float* out_f32; long long ld_out_f32;
+  __nv_bfloat16* out_bf16; long long ld_out_bf16;
+  int vec_a, vec_w;      // 1: rows are 16-byte (fp32) / 8-byte (bf16) aligned and K % 4 == 0
+};
+
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* base, long long ld, int row, int rows, int k, int K, int vec);
+
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* base, long long ld, int row, int rows, int k, int K, int vec) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= rows) return r;
+  const float* p = base + (long long)row * ld + k;
+  if (vec && k + 3 < K) return *reinterpret_cast<const float4*>(p);
+  if (k + 0 < K) r.x = p[0];
+  if (k + 1 < K) r.y = p[1];
+  if (k + 2 < K) r.z = p[2];
+  if (k + 3 < K) r.w = p[3];
+  return r;
+}
+
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* base, long long ld, int row, int rows,
+                                                       int k, int K, int vec) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= rows) return r;
+  const __nv_bfloat16* p = base + (long long)row * ld + k;
+  if (vec && k + 3 < K) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+  if (k + 0 < K) r.x = __bfloat162float(p[0]);
+  if (k + 1 < K) r.y = __bfloat162float(p[1]);
+  if (k + 2 < K) r.z = __bfloat162float(p[2]);
+  if (k + 3 < K) r.w = __bfloat162float(p[3]);
+  return r;
+}
+
+template <typename TA, typename TW>
+__global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) {
+  __shared__ __align__(16) float As[BK][BM];
+  __shared__ __align__(16) float Ws[BK][BN];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const TA* A = static_cast<const TA*>(p.A);
+  const TW* W = static_cast<const TW*>(p.W);
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    if (tid < 128) {                        // A tile: 32 rows x 16 k
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+      float4 v = load4<TA>(A, p.lda, m0 + r, p.M, k0 + kq, p.K, p.vec_a);
+      As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {           // W tile: 256 rows x 16 k
+      const int kq = i * 4;
+      float4 v = load4<TW>(W, p.ldw, n0 + tid, p.N, k0 + kq, p.K, p.vec_w);
+      Ws[kq + 0][tid] = v.x; Ws[kq + 1][tid] = v.y; Ws[kq + 2][tid] = v.z; Ws[kq + 3][tid] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][warp * 4]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k][lane * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[k][lane * 8 + 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ---------------------------------------------------------------------------------
+  const int nbase = n0 + lane * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + warp * 4 + i;
+    if (m >= p.M) continue;                 // warp-uniform
+    float y[8];
+    const bool gate = p.row_gate ? (p.row_gate[m] != 0) : true;
+    const float* rb = p.row_bias ? p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = nbase + j;
+      float v = 0.f;
+      if (n < p.N) {
+        v = acc[i][j];
+        if (p.bias) v += p.bias[n];
+        if (rb) v += rb[n];
+        if (!gate) v = 0.f;
+        if (p.residual) v += p.residual[(long long)m * p.ld_residual + n];
+        if (p.residual2) v += p.residual2[(long long)m * p.ld_residual2 + n];
+      }
+      y[j] = v;
+    }
+    if (p.ln_gamma) {                       // whole row is inside this warp (host guarantees N <= 256)
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += (nbase + j < p.N) ? y[j] : 0.f;
+      const float mean = warp_sum(s) / (float)p.N;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = (nbase + j < p.N) ? y[j] - mean : 0.f;
+        sq += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(sq) / (float)p.N + p.ln_eps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = nbase + j;
+        if (n < p.N) y[j] = (y[j] - mean) * rstd * p.ln_gamma[n] + p.ln_beta[n];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = nbase + j;
+      if (n >= p.N) continue;
+      float v = p.relu ? fmaxf(y[j], 0.f) : y[j];
+      if (p.post_add) v += p.post_add[(long long)m * p.ld_post_add + n];
+      if (p.out_f32) p.out_f32[(long long)m * p.ld_out_f32 + n] = v;
+      if (p.out_bf16) p.out_bf16[(long long)m * p.ld_out_bf16 + n] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ---- fused 3 -> C point embedding: ReLU(LN(Linear3(f(x)))) ---------------------------------------
+struct PointEmbedParams {
+  const float* x; long long ldx; int M, C, logit;
+  const float* weight; const float* bias; const float* gamma; const float* beta; float eps;
+  float* out_f32; __nv_bfloat16* out_bf16;
+};
+
+constexpr int kPeMaxPerLane = 32;   // C <= 1024
+
+__global__ void __launch_bounds__(128) point_embed_kernel(const PointEmbedParams p) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (m >= p.M) return;
+  float x0 = p.x[(long long)m * p.ldx + 0], x1 = p.x[(long long)m * p.ldx + 1], x2 = p.x[(long long)m * p.ldx + 2];
+  if (p.logit) { x0 = logit_f32(x0); x1 = logit_f32(x1); x2 = logit_f32(x2); }
+  const int per = p.C >> 5;
+  float y[kPeMaxPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kPeMaxPerLane; ++j) {
+    if (j < per) {
+      const int c = j * 32 + lane;
+      // x . w in k order, then + bias (addmm: bias + x W^T; K = 3)
+      float v = fmaf(x2, p.weight[c * 3 + 2], fmaf(x1, p.weight[c * 3 + 1], x0 * p.weight[c * 3 + 0])) + p.bias[c];
+      y[j] = v;
+      s += v;
+    }
+  }
+  const float mean = warp_sum(s) / (float)p.C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < kPeMaxPerLane; ++j)
+    if (j < per) { const float d = y[j] - mean; sq += d * d; }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)p.C + p.eps);
+#pragma unroll
+  for (int j = 0; j < kPeMaxPerLane; ++j) {
+    if (j < per) {
+      const int c = j * 32 + lane;
+      const float v = fmaxf((y[j] - mean) * rstd * p.gamma[c] + p.beta[c], 0.f);
+      if (p.out_f32) p.out_f32[(long long)m * p.C + c] = v;
+      if (p.out_bf16) p.out_bf16[(long long)m * p.C + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+}  // namespace
+
+int linear_simt_launch(const tc_linear_args* a, cudaStream_t s) {
+  LinearParams p;
+  p.A = a->A; p.lda = a->lda; p.W = a->W; p.ldw = a->ldw;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.bias = a->bias;
+  p.row_bias = a->row_bias; p.row_bias_period = a->row_bias_period > 0 ? a->row_bias_period : 1;
+  p.ld_row_bias = a->ld_row_bias;
+  p.row_gate = a->row_gate;
+  p.residual = a->residual; p.ld_residual = a->ld_residual;
+  p.residual2 = a->residual2; p.ld_residual2 = a->ld_residual2;
+  p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_eps = a->ln_eps;
+  p.relu = a->relu;
+  p.post_add = a->post_add; p.ld_post_add = a->ld_post_add;
+  p.out_f32 = a->out_f32; p.ld_out_f32 = a->ld_out_f32;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); p.ld_out_bf16 = a->ld_out_bf16;
+  const int ea = a->a_dtype == TC_BF16 ? 2 : 4, ew = a->w_dtype == TC_BF16 ? 2 : 4;
+  p.vec_a = (a->K % 4 == 0) && ((a->lda * ea) % (4 * ea) == 0) && ((reinterpret_cast<uintptr_t>(a->A) % (4 * ea)) == 0);
+  p.vec_w = (a->K % 4 == 0) && ((a->ldw * ew) % (4 * ew) == 0) && ((reinterpret_cast<uintptr_t>(a->W) % (4 * ew)) == 0);
+  dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN);
+  if (a->a_dtype == TC_F32 && a->w_dtype == TC_F32) linear_simt_kernel<float, float><<<grid, 256, 0, s>>>(p);
+  else if (a->a_dtype == TC_BF16 && a->w_dtype == TC_BF16) linear_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(p);
+  else if (a->a_dtype == TC_F32 && a->w_dtype == TC_BF16) linear_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>(p);
+  else linear_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>(p);
+  count_launch();
+  return check_launch("tc_linear(simt)");
+}
+
+}  // namespace tc
+
+extern "C" int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_point_embed: args is NULL");
+  TC_REQUIRE(a->x && a->weight && a->bias && a->ln_gamma && a->ln_beta, TC_ERR_NULL, "tc_point_embed: NULL pointer");
+  TC_REQUIRE(a->out_f32 || a->out_bf16, TC_ERR_NULL, "tc_point_embed: no output");
+  TC_REQUIRE(a->C > 0 && a->C % 32 == 0 && a->C <= 32 * kPeMaxPerLane, TC_ERR_SHAPE, "tc_point_embed: bad C %d", a->C);
+  TC_REQUIRE(a->M >= 0 && a->ldx >= 3, TC_ERR_SHAPE, "tc_point_embed: bad M/ldx");
+  if (a->M == 0) return TC_OK;
+  PointEmbedParams p{a->x, a->ldx, a->M, a->C, a->logit_input, a->weight, a->bias, a->ln_gamma, a->ln_beta,
+                     a->ln_eps, a->out_f32, static_cast<__nv_bfloat16*>(a->out_bf16)};
+  point_embed_kernel<<<(a->M + 3) / 4, 128, 0, as_stream(stream)>>>(p);
+  count_launch();
+  return check_launch("tc_point_embed");
+}

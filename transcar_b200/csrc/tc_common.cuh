@@ -1,0 +1,98 @@
+// Shared device/host helpers for the transcar_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/transcar_b200.h"
+
+namespace tc {
+
+// ---- host-side error plumbing (capi.cu owns the storage) -------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);     // returns cudaGetLastError() (0 = ok) and records the message
+
+#define TC_REQUIRE(cond, code, ...)            \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::tc::set_error(__VA_ARGS__);            \
+      return (code);                           \
+    }                                          \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline cudaStream_t as_stream(tc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// torch.sigmoid in fp32: 1 / (1 + exp(-x)) with the full-precision expf.
+__device__ __forceinline__ float sigmoid_f32(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// inverse_sigmoid (T:17-32): clamp to [0,1], eps 1e-5 on numerator and denominator, log of the ratio.
+__device__ __forceinline__ float logit_f32(float x) {
+  x = fminf(fmaxf(x, 0.0f), 1.0f);
+  float a = fmaxf(x, 1e-5f);
+  float b = fmaxf(__fsub_rn(1.0f, x), 1e-5f);
+  return logf(__fdiv_rn(a, b));
+}
+
+// 128-bit read-only global load that does not allocate in L1 (streaming gathers).
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- radar distance mask: one (query circle set, radar point) test --------------------------------
+// torch.cdist(p=2) on [900,2]x[1500,2] takes the matmul route (_euclidean_dist):
+//   x_ = [-2*x0, -2*x1, |x|^2, 1]   y_ = [y0, y1, 1, |y|^2]   d = sqrt(clamp_min(x_ . y_, 0))
+// The dot product is restated as an fp32 FMA chain in k order (what a K=4 SGEMM does); the norms are
+// rounded squares added without contraction (pow(2) and sum are separate ATen kernels).
+struct Circle { float m2x, m2y, nrm; };     // -2*cx, -2*cy, cx^2+cy^2
+
+__device__ __forceinline__ Circle make_circle(float cx, float cy) {
+  Circle c;
+  c.m2x = __fmul_rn(cx, -2.0f);
+  c.m2y = __fmul_rn(cy, -2.0f);
+  c.nrm = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy));
+  return c;
+}
+__device__ __forceinline__ float key_norm(float kx, float ky) {
+  return __fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky));
+}
+__device__ __forceinline__ float cdist_mm(const Circle& c, float kx, float ky, float knrm) {
+  float acc = __fmul_rn(c.m2x, kx);
+  acc = __fmaf_rn(c.m2y, ky, acc);
+  acc = __fmaf_rn(c.nrm, 1.0f, acc);
+  acc = __fmaf_rn(1.0f, knrm, acc);
+  return __fsqrt_rn(fmaxf(acc, 0.0f));
+}
+// geom = (cx, cy, fx, fy, rx, ry, radius, -)
+__device__ __forceinline__ bool radar_allowed(const Circle& c, const Circle& f, const Circle& r, float radius,
+                                              float kx, float ky, float knrm) {
+  return (cdist_mm(c, kx, ky, knrm) < radius) | (cdist_mm(f, kx, ky, knrm) < radius) |
+         (cdist_mm(r, kx, ky, knrm) < radius);
+}
+
+}  // namespace tc

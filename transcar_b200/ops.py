@@ -1,0 +1,295 @@
+"""Torch-tensor front end of the C ABI: PyTorch owns memory and streams, the library does the math.
+
+Every function enqueues on ``torch.cuda.current_stream()`` and returns immediately.  Inputs must be
+CUDA tensors; nothing here computes with torch ops and nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import TC_BF16, TC_F32
+
+_DT = {torch.float32: TC_F32, torch.bfloat16: TC_BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need(t, name, dtype=None, last_contig=True):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"transcar_b200: `{name}` must be a CUDA tensor (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"transcar_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if last_contig and t.dim() > 0 and t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise RuntimeError(f"transcar_b200: `{name}` must be contiguous in its last dimension")
+    return t
+
+
+def _rows(t, name):
+    """2-D view [M, N] with a uniform row stride; returns (tensor, ld)."""
+    if t.dim() != 2:
+        t = t.reshape(-1, t.shape[-1])
+    _need(t, name)
+    return t, t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+# --------------------------------------------------------------------------------------- K1
+def is_channels_last_5d(f):
+    """logical [B,N,C,H,W] stored as [B,N,H,W,C]"""
+    B, N, Cc, H, W = f.shape
+    return f.stride() == (N * H * W * Cc, H * W * Cc, 1, W * Cc, Cc)
+
+
+def to_channels_last(f, dtype=None):
+    """[B,N,C,H,W] in any layout -> same logical tensor stored channels-last, via tc_nchw_to_nhwc when a
+    physical re-layout is needed (fp32 NCHW input).  Zero-copy when already channels-last."""
+    dtype = dtype or f.dtype
+    if is_channels_last_5d(f) and f.dtype == dtype:
+        return f
+    B, N, Cc, H, W = f.shape
+    if f.dtype != torch.float32 or not f.is_contiguous():
+        raise RuntimeError("transcar_b200: feature maps must be channels-last (any dtype) or contiguous NCHW fp32")
+    _need(f, "feat")
+    out = torch.empty((B, N, H, W, Cc), device=f.device, dtype=dtype)
+    lib = _lib.load()
+    _lib.check(lib.tc_nchw_to_nhwc(_ptr(f), _ptr(out), _DT[dtype], B * N, Cc, H * W, _stream()), "nchw_to_nhwc")
+    return out.permute(0, 1, 4, 2, 3)
+
+
+def sample_fwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, out_dtype=torch.float32,
+               want_mask=False, out=None):
+    """feats: 4 x logical [B,N,C,H,W] channels-last; ref [B,Q,3]; lidar2img [B,N,4,4]; attn_logits [B,Q,N*L].
+    Returns (out [B,Q,C], mask [B,Q,N] uint8 or None)."""
+    lib = _lib.load()
+    a = _lib.SampleArgs()
+    B, N, Cc = feats[0].shape[:3]
+    Q = ref.shape[1]
+    if len(feats) != 4:
+        raise RuntimeError("transcar_b200.sample_fwd: exactly 4 feature levels are supported")
+    for l, f in enumerate(feats):
+        _need(f, f"feats[{l}]", last_contig=False)
+        if not is_channels_last_5d(f):
+            raise RuntimeError(f"transcar_b200.sample_fwd: feats[{l}] is not channels-last; use ops.to_channels_last")
+        if f.dtype != feats[0].dtype or f.shape[:3] != feats[0].shape[:3]:
+            raise RuntimeError("transcar_b200.sample_fwd: feature levels disagree in dtype / batch / cams / channels")
+        a.feat[l] = f.data_ptr()
+        a.H[l], a.W[l] = f.shape[3], f.shape[4]
+    ref = _need(ref, "ref", torch.float32).contiguous()
+    lidar2img = _need(lidar2img, "lidar2img", torch.float32).contiguous()
+    attn_logits = _need(attn_logits, "attn_logits", torch.float32).contiguous()
+    assert ref.shape == (B, Q, 3) and lidar2img.shape == (B, N, 4, 4) and attn_logits.shape == (B, Q, N * 4)
+    if out is None:
+        out = torch.empty((B, Q, Cc), device=ref.device, dtype=out_dtype)
+    mask = torch.empty((B, Q, N), device=ref.device, dtype=torch.uint8) if want_mask else None
+    a.num_levels, a.B, a.N, a.Q, a.C = 4, B, N, Q, Cc
+    a.feat_dtype, a.out_dtype = _DT[feats[0].dtype], _DT[out.dtype]
+    a.ref, a.lidar2img, a.attn_logits = ref.data_ptr(), lidar2img.data_ptr(), attn_logits.data_ptr()
+    for i in range(6):
+        a.pc_range[i] = float(pc_range[i])
+    a.img_w, a.img_h = float(img_w), float(img_h)
+    a.out = out.data_ptr()
+    a.mask = mask.data_ptr() if mask is not None else None
+    _lib.check(lib.tc_sample_fwd(C.byref(a), _stream()), "sample_fwd")
+    return out, mask
+
+
+# --------------------------------------------------------------------------------------- K3
+def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, residual=None, residual2=None,
+           ln=None, ln_eps=1e-5, relu=False, post_add=None, out_f32=None, out_bf16=None,
+           want_f32=True, want_bf16=False):
+    """Y = epilogue(A @ W^T) - see ``tc_linear`` in include/transcar_b200.h.  A [M,K], W [N,K].
+    ``ln`` = (gamma, beta).  Returns (out_f32 or None, out_bf16 or None)."""
+    lib = _lib.load()
+    A, lda = _rows(_need(A, "A"), "A")
+    W, ldw = _rows(_need(W, "W"), "W")
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K, (A.shape, W.shape)
+    a = _lib.LinearArgs()
+    a.A, a.a_dtype, a.lda = A.data_ptr(), _DT[A.dtype], lda
+    a.W, a.w_dtype, a.ldw = W.data_ptr(), _DT[W.dtype], ldw
+    a.M, a.N, a.K = M, N, K
+    keep = [A, W]
+    if bias is not None:
+        a.bias = _need(bias, "bias", torch.float32).data_ptr()
+    if row_bias is not None:
+        rb, ldrb = _rows(_need(row_bias, "row_bias", torch.float32), "row_bias")
+        a.row_bias, a.ld_row_bias = rb.data_ptr(), ldrb
+        a.row_bias_period = row_bias_period or rb.shape[0]
+        keep.append(rb)
+    if row_gate is not None:
+        a.row_gate = _need(row_gate, "row_gate", torch.uint8).data_ptr()
+    if residual is not None:
+        r, ldr = _rows(_need(residual, "residual", torch.float32), "residual")
+        a.residual, a.ld_residual = r.data_ptr(), ldr
+        keep.append(r)
+    if residual2 is not None:
+        r2, ldr2 = _rows(_need(residual2, "residual2", torch.float32), "residual2")
+        a.residual2, a.ld_residual2 = r2.data_ptr(), ldr2
+        keep.append(r2)
+    if ln is not None:
+        a.ln_gamma = _need(ln[0], "ln_gamma", torch.float32).data_ptr()
+        a.ln_beta = _need(ln[1], "ln_beta", torch.float32).data_ptr()
+        a.ln_eps = float(ln_eps)
+    a.relu = 1 if relu else 0
+    if post_add is not None:
+        pa, ldpa = _rows(_need(post_add, "post_add", torch.float32), "post_add")
+        a.post_add, a.ld_post_add = pa.data_ptr(), ldpa
+        keep.append(pa)
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    if out_bf16 is None and want_bf16:
+        out_bf16 = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
+    if out_f32 is not None:
+        o, ldo = _rows(_need(out_f32, "out_f32", torch.float32), "out_f32")
+        a.out_f32, a.ld_out_f32 = o.data_ptr(), ldo
+    if out_bf16 is not None:
+        o, ldo = _rows(_need(out_bf16, "out_bf16", torch.bfloat16), "out_bf16")
+        a.out_bf16, a.ld_out_bf16 = o.data_ptr(), ldo
+    _lib.check(lib.tc_linear(C.byref(a), _stream()), "linear")
+    return out_f32, out_bf16
+
+
+def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, want_f32=True, want_bf16=False):
+    """ReLU(LN(Linear_{3->C}(f(x[:, :3])))); x [M, ldx>=3] fp32."""
+    lib = _lib.load()
+    x, ldx = _rows(_need(x, "x", torch.float32), "x")
+    M, Cc = x.shape[0], weight.shape[0]
+    a = _lib.PointEmbedArgs()
+    a.x, a.ldx, a.M, a.C, a.logit_input = x.data_ptr(), ldx, M, Cc, 1 if logit_input else 0
+    a.weight = _need(weight, "weight", torch.float32).contiguous().data_ptr()
+    a.bias = _need(bias, "bias", torch.float32).data_ptr()
+    a.ln_gamma = _need(ln_gamma, "ln_gamma", torch.float32).data_ptr()
+    a.ln_beta = _need(ln_beta, "ln_beta", torch.float32).data_ptr()
+    a.ln_eps = float(ln_eps)
+    o32 = torch.empty((M, Cc), device=x.device, dtype=torch.float32) if want_f32 else None
+    o16 = torch.empty((M, Cc), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    a.out_f32, a.out_bf16 = _ptr(o32), _ptr(o16)
+    _lib.check(lib.tc_point_embed(C.byref(a), _stream()), "point_embed")
+    return o32, o16
+
+
+# --------------------------------------------------------------------------------------- K4
+def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_row_any=False, scale=None, out=None):
+    """q [B,Lq,E], k/v [B,Lk,E] (views with a row stride are fine) -> out [B,Lq,E], row_any [B,Lq] or None."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, n)
+        if t.dim() != 3:
+            raise RuntimeError(f"transcar_b200.attention: `{n}` must be [B, L, E]")
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    D = E // heads
+    out_dtype = out_dtype or q.dtype
+    if out is None:
+        out = torch.empty((B, Lq, E), device=q.device, dtype=out_dtype)
+    a = _lib.AttentionArgs()
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.ldq, a.ldk, a.ldv = q.stride(1), k.stride(1), v.stride(1)
+    a.q_batch_stride, a.k_batch_stride, a.v_batch_stride = q.stride(0), k.stride(0), v.stride(0)
+    a.qkv_dtype = _DT[q.dtype]
+    a.B, a.Lq, a.Lk, a.heads, a.D = B, Lq, Lk, heads, D
+    a.scale = float(scale if scale is not None else 1.0 / math.sqrt(D))
+    if geom is not None:
+        geom = _need(geom, "geom", torch.float32).contiguous()
+        key_xy = _need(key_xy, "key_xy", torch.float32).contiguous()
+        assert geom.shape[-1] == 8 and geom.numel() == B * Lq * 8 and key_xy.numel() == B * Lk * 2
+        a.geom, a.key_xy = geom.data_ptr(), key_xy.data_ptr()
+    row_any = torch.empty((B, Lq), device=q.device, dtype=torch.uint8) if want_row_any else None
+    a.out, a.ldo, a.out_dtype = out.data_ptr(), out.stride(1), _DT[out.dtype]
+    a.row_any = _ptr(row_any)
+    _lib.check(lib.tc_attention_fwd(C.byref(a), _stream()), "attention")
+    return out, row_any
+
+
+def radar_geometry(centre, code, pc_range, r_lo, r_hi, centre_is_normalised):
+    """centre [M, >=2], code [M, >=8] fp32 -> geom [M, 8]."""
+    lib = _lib.load()
+    centre, ldc = _rows(_need(centre, "centre", torch.float32), "centre")
+    code, ldk = _rows(_need(code, "code", torch.float32), "code")
+    M = centre.shape[0]
+    geom = torch.empty((M, 8), device=centre.device, dtype=torch.float32)
+    a = _lib.RadarGeometryArgs()
+    a.centre, a.ld_centre, a.centre_is_normalised = centre.data_ptr(), ldc, 1 if centre_is_normalised else 0
+    a.code, a.ld_code, a.M = code.data_ptr(), ldk, M
+    for i in range(6):
+        a.pc_range[i] = float(pc_range[i])
+    a.r_lo, a.r_hi = float(r_lo), float(r_hi)
+    a.geom = geom.data_ptr()
+    _lib.check(lib.tc_radar_geometry(C.byref(a), _stream()), "radar_geometry")
+    return geom
+
+
+def radar_mask(geom, key_xy, B, Lq, Lk, want_blocked=True):
+    """Materialised ``blocked [B,Lq,Lk]`` uint8 (1 = not attended) + ``row_any [B,Lq]`` - test aid."""
+    lib = _lib.load()
+    geom = _need(geom, "geom", torch.float32).contiguous()
+    key_xy = _need(key_xy, "key_xy", torch.float32).contiguous()
+    blocked = torch.empty((B, Lq, Lk), device=geom.device, dtype=torch.uint8) if want_blocked else None
+    row_any = torch.empty((B, Lq), device=geom.device, dtype=torch.uint8)
+    _lib.check(lib.tc_radar_mask(_ptr(geom), _ptr(key_xy), B, Lq, Lk, _ptr(blocked), _ptr(row_any), _stream()),
+               "radar_mask")
+    return blocked, row_any
+
+
+# --------------------------------------------------------------------------------------- pointwise
+def ref_update(code, ref, out=None):
+    """code [M, >=5], ref [M,3] -> new ref [M,3] (T:195-203)."""
+    lib = _lib.load()
+    code, ldc = _rows(_need(code, "code", torch.float32), "code")
+    ref = _need(ref, "ref", torch.float32).contiguous()
+    M = code.shape[0]
+    if out is None:
+        out = torch.empty((M, 3), device=code.device, dtype=torch.float32)
+    _lib.check(lib.tc_ref_update(_ptr(code), ldc, _ptr(ref), _ptr(out), M, _stream()), "ref_update")
+    return out
+
+
+def box_anchor_add(code, anchor, xy_col, z_col, xy_from_normalised, pc_range):
+    """In place: code[:,0:2] += anchor_xy(metres), code[:,4] += anchor_z (H:596-600, :664-665, :722-723)."""
+    lib = _lib.load()
+    code, ldc = _rows(_need(code, "code", torch.float32), "code")
+    anchor, lda = _rows(_need(anchor, "anchor", torch.float32), "anchor")
+    pc = (C.c_float * 6)(*[float(x) for x in pc_range])
+    _lib.check(lib.tc_box_anchor_add(_ptr(code), ldc, _ptr(anchor), lda, xy_col, z_col,
+                                     1 if xy_from_normalised else 0, C.byref(pc), code.shape[0], _stream()),
+               "box_anchor_add")
+    return code
+
+
+def cast_bf16(src):
+    lib = _lib.load()
+    s, lds = _rows(_need(src, "src", torch.float32), "src")
+    dst = torch.empty(s.shape, device=s.device, dtype=torch.bfloat16)
+    _lib.check(lib.tc_cast_bf16(_ptr(s), lds, _ptr(dst), dst.stride(0) if dst.shape[0] > 1 else dst.shape[1],
+                                s.shape[0], s.shape[1], _stream()), "cast_bf16")
+    return dst.view(src.shape)
+
+
+def decode(cls, code, max_num, post_center_range):
+    """cls [B,Q,classes], code [B,Q,10] fp32 -> boxes [B,max_num,9], scores, labels (int32), keep (uint8)."""
+    lib = _lib.load()
+    cls = _need(cls, "cls", torch.float32).contiguous()
+    code = _need(code, "code", torch.float32).contiguous()
+    B, Q, classes = cls.shape
+    dev = cls.device
+    boxes = torch.empty((B, max_num, 9), device=dev, dtype=torch.float32)
+    scores = torch.empty((B, max_num), device=dev, dtype=torch.float32)
+    labels = torch.empty((B, max_num), device=dev, dtype=torch.int32)
+    keep = torch.empty((B, max_num), device=dev, dtype=torch.uint8)
+    a = _lib.DecodeArgs()
+    a.cls, a.code, a.B, a.Q, a.classes, a.max_num = cls.data_ptr(), code.data_ptr(), B, Q, classes, max_num
+    for i in range(6):
+        a.post_center_range[i] = float(post_center_range[i])
+    a.boxes, a.scores, a.labels, a.keep = boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), keep.data_ptr()
+    _lib.check(lib.tc_decode(C.byref(a), _stream()), "decode")
+    return boxes, scores, labels, keep
