@@ -60,6 +60,7 @@ def test_argument_validation_without_gpu():
     a.N = 0
     assert lib.tc_linear(ctypes.byref(a), None) == -2
     s = _lib.SampleArgs()
+    s.B, s.Q = 1, 1
     assert lib.tc_sample_fwd(ctypes.byref(s), None) == -1
     at = _lib.AttentionArgs()
     at.q = at.k = at.v = at.out = ctypes.addressof(buf)

@@ -58,6 +58,9 @@ extern "C" int tc_check_device(void) {
 extern "C" int tc_linear(const tc_linear_args* a, tc_stream_t stream) {
   using namespace tc;
   TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_linear: args is NULL");
+  TC_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, TC_ERR_SHAPE, "tc_linear: bad M/N/K %d/%d/%d", a->M, a->N, a->K);
+  TC_REQUIRE(!a->ln_gamma || a->N <= 256, TC_ERR_SHAPE, "tc_linear: fused LayerNorm needs N <= 256 (got %d)", a->N);
+  if (a->M == 0) return TC_OK;                      // empty row set: nothing to do (pointers may be NULL)
   TC_REQUIRE(a->A && a->W, TC_ERR_NULL, "tc_linear: A or W is NULL");
   TC_REQUIRE(a->out_f32 || a->out_bf16, TC_ERR_NULL, "tc_linear: no output pointer");
   TC_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, TC_ERR_SHAPE, "tc_linear: bad M/N/K %d/%d/%d", a->M, a->N, a->K);

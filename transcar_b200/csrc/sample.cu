@@ -129,10 +129,12 @@ sample_kernel(const SampleParams p) {
   bool valid = false;
   if (lane < p.N) {
     const float* m = s_mat + lane * 16;
-    // 4x4 . (px,py,pz,1): k-ordered fp32 FMA chain (a K=4 SGEMM row)
-    float cx = __fmaf_rn(m[3], 1.0f, __fmaf_rn(m[2], pz, __fmaf_rn(m[1], py, __fmul_rn(m[0], px))));
-    float cy = __fmaf_rn(m[7], 1.0f, __fmaf_rn(m[6], pz, __fmaf_rn(m[5], py, __fmul_rn(m[4], px))));
-    float cz = __fmaf_rn(m[11], 1.0f, __fmaf_rn(m[10], pz, __fmaf_rn(m[9], py, __fmul_rn(m[8], px))));
+    // 4x4 . (px,py,pz,1) in the evaluation order of the batched K=4 SGEMM that torch.matmul dispatches to on
+    // sm_100 (found by tools/probe_matmul4.py: bit-identical on 21600/21600 outputs):
+    //   (m0*px (+) m1*py)  +  (m2*pz (+) m3*1)   with (+) = FMA
+    float cx = __fadd_rn(__fmaf_rn(m[1], py, __fmul_rn(m[0], px)), __fmaf_rn(m[3], 1.0f, __fmul_rn(m[2], pz)));
+    float cy = __fadd_rn(__fmaf_rn(m[5], py, __fmul_rn(m[4], px)), __fmaf_rn(m[7], 1.0f, __fmul_rn(m[6], pz)));
+    float cz = __fadd_rn(__fmaf_rn(m[9], py, __fmul_rn(m[8], px)), __fmaf_rn(m[11], 1.0f, __fmul_rn(m[10], pz)));
     const float eps = 1e-5f;
     valid = cz > eps;
     const float zc = fmaxf(cz, eps);
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   using namespace tc;
   TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_sample_fwd: args is NULL");
+  if (a->B == 0 || a->Q == 0) return TC_OK;         // empty batch / query set: nothing to do
   TC_REQUIRE(a->ref && a->lidar2img && a->attn_logits && a->out, TC_ERR_NULL, "tc_sample_fwd: NULL tensor pointer");
   TC_REQUIRE(a->num_levels == 4, TC_ERR_SHAPE, "tc_sample_fwd: num_levels must be 4 (got %d)", a->num_levels);
   TC_REQUIRE(a->N >= 1 && a->N <= TC_MAX_CAMS && a->N * a->num_levels <= 32, TC_ERR_SHAPE,
