@@ -318,7 +318,7 @@ class Detr3DTransformer(nn.Module):
             self._engine_key = key
         eng = self._engine
         B = mlvl_feats[0].shape[0]
-        feats, l2i, img_w, img_h, _ = eng.prepare_inputs(mlvl_feats, kwargs["img_metas"])
+        feats, l2i, img_w, img_h, _, _ = eng.prepare_inputs(mlvl_feats, kwargs["img_metas"])
         hs, refs, *_ = eng.decoder(feats, l2i, img_w, img_h, B, keep_all=True)
         Q, C = eng.Q, eng.C
         inter_states = torch.stack([h.view(B, Q, C).permute(1, 0, 2) for h in hs])
