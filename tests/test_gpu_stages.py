@@ -82,13 +82,17 @@ def test_sample_fp32_vs_oracle(ops, config, B, Q):
     torch.testing.assert_close(out.cpu(), want_c, rtol=0, atol=1e-4)
 
 
-def test_sample_smooth_feats_1e5_vs_cpu_oracle(ops):
+def test_sample_smooth_feats_vs_cpu_and_gpu_oracle(ops):
     feats, metas, ref, logits = _sampling_case(2, 256, "tiny", seed=9, smooth=True)
     l2i = torch.tensor(np.asarray([m["lidar2img"] for m in metas]), dtype=torch.float32, device=dev())
     cl = [ops.to_channels_last(f.to(dev())) for f in feats]
     out, _ = ops.sample_fwd(cl, ref.to(dev()), l2i, logits.to(dev()), synthetic.PC_RANGE, 1600, 928)
     want_c, _ = _oracle_sampled_sum(feats, metas, ref, logits, "cpu")
-    torch.testing.assert_close(out.cpu(), want_c, rtol=0, atol=1e-5)
+    # the kernel follows ATen's CUDA arithmetic (x * (1/1600), CUDA un-normalisation); ATen's CPU kernels round
+    # these two steps differently, which shows as ~1e-5 on band-limited features
+    torch.testing.assert_close(out.cpu(), want_c, rtol=0, atol=3e-5)
+    want_g, _ = _oracle_sampled_sum(feats, metas, ref, logits, dev())
+    torch.testing.assert_close(out, want_g, rtol=0, atol=1e-5)
 
 
 def test_sample_bf16_and_layouts(ops):

@@ -26,7 +26,7 @@ struct SampleParams {
   const float* lidar2img;
   const float* logits;
   float pc[6];
-  float img_w, img_h;
+  float inv_w, inv_h;      // 1.0f / img_w, 1.0f / img_h
   void* out;
   uint8_t* mask;
 };
@@ -138,8 +138,10 @@ sample_kernel(const SampleParams p) {
     const float eps = 1e-5f;
     valid = cz > eps;
     const float zc = fmaxf(cz, eps);
-    float u = __fdiv_rn(__fdiv_rn(cx, zc), p.img_w);
-    float v = __fdiv_rn(__fdiv_rn(cy, zc), p.img_h);
+    // `x /= python_scalar` on a CUDA tensor is x * (1/scalar) in ATen (BinaryDivTrueKernel: cpu-scalar fast path),
+    // not a true division; tensor / tensor (the perspective divide) is IEEE division.
+    float u = __fmul_rn(__fdiv_rn(cx, zc), p.inv_w);
+    float v = __fmul_rn(__fdiv_rn(cy, zc), p.inv_h);
     gx = __fmul_rn(__fadd_rn(u, -0.5f), 2.0f);
     gy = __fmul_rn(__fadd_rn(v, -0.5f), 2.0f);
     valid = valid && (gx > -1.0f) && (gx < 1.0f) && (gy > -1.0f) && (gy < 1.0f);
@@ -267,7 +269,7 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   p.B = a->B; p.N = a->N; p.Q = a->Q; p.C = a->C;
   p.ref = a->ref; p.lidar2img = a->lidar2img; p.logits = a->attn_logits;
   for (int i = 0; i < 6; ++i) p.pc[i] = a->pc_range[i];
-  p.img_w = a->img_w; p.img_h = a->img_h;
+  p.inv_w = 1.0f / a->img_w; p.inv_h = 1.0f / a->img_h;
   p.out = a->out; p.mask = a->mask;
   dim3 grid((a->Q + kWarpsPerBlock - 1) / kWarpsPerBlock, a->B);
   dim3 block(kWarpsPerBlock * 32);
