@@ -39,6 +39,7 @@ struct EpiParams {
   const float* post_add; long long ld_post_add;
   float* out_f32; long long ld_out_f32;
   __nv_bfloat16* out_bf16; long long ld_out_bf16;
+  int vec;        // 1: N % 32 == 0 and every row-wise operand is 16-byte aligned -> 128-bit epilogue accesses
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -213,17 +214,98 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    // Math is one accumulator row per thread (tcgen05.ld 32x32b); every global read/write of a row-major
+    // operand goes through a per-warp 32x32 shared-memory tile so that each warp instruction touches whole
+    // 128-byte row segments (the pipeline stages are free once the accumulator barrier has fired).
     const int quad = warp & 3;
-    const int m = m0 + quad * 32 + lane;
+    const int row0 = m0 + quad * 32;            // first row of this warp
+    const int m = row0 + lane;
     const bool row_ok = m < p.M;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
     mbar_wait(accbar, 0);
     tc_fence_after();
+    float (*tile)[33] = reinterpret_cast<float (*)[33]>(smem + (warp - 2) * 4352);
+    const bool vec = p.vec != 0;
+
+    // coalesced [32 rows x 32 cols] fp32 tile -> this thread's row.  row r of the warp lives at base + rowoff(r).
+    auto stage_in = [&](const float* base, long long ld, int period, int n, float (&t)[32]) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3), c = (lane & 7) * 4;
+        const int gm = row0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gm < p.M) {
+          const float* src = base + (long long)(period > 0 ? gm % period : gm) * ld + n + c;
+          if (vec) {
+            v = *reinterpret_cast<const float4*>(src);
+          } else {
+            if (n + c + 0 < p.N) v.x = src[0];
+            if (n + c + 1 < p.N) v.y = src[1];
+            if (n + c + 2 < p.N) v.z = src[2];
+            if (n + c + 3 < p.N) v.w = src[3];
+          }
+        }
+        tile[r][c + 0] = v.x; tile[r][c + 1] = v.y; tile[r][c + 2] = v.z; tile[r][c + 3] = v.w;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = tile[lane][j];
+    };
+    // per-column vector (bias / gamma / beta): same addresses for the whole warp -> broadcast loads
+    auto load_vec = [&](const float* base, int n, float (&t)[32]) {
+      if (vec) {
+        load32(base + n, t);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = (n + j < p.N) ? base[n + j] : 0.f;
+      }
+    };
+    auto stage_out = [&](int n, const float (&v)[32]) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tile[lane][j] = v[j];
+      __syncwarp();
+      if (p.out_f32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3), c = (lane & 7) * 4;
+          const int gm = row0 + r;
+          if (gm < p.M) {
+            float* dst = p.out_f32 + (long long)gm * p.ld_out_f32 + n + c;
+            if (vec) {
+              *reinterpret_cast<float4*>(dst) = make_float4(tile[r][c], tile[r][c + 1], tile[r][c + 2], tile[r][c + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (n + c + k < p.N) dst[k] = tile[r][c + k];
+            }
+          }
+        }
+      }
+      if (p.out_bf16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2), c = (lane & 3) * 8;
+          const int gm = row0 + r;
+          if (gm < p.M) {
+            __nv_bfloat16* dst = p.out_bf16 + (long long)gm * p.ld_out_bf16 + n + c;
+            if (vec) {
+              uint4 u;
+              u.x = pack_bf16(tile[r][c + 0], tile[r][c + 1]); u.y = pack_bf16(tile[r][c + 2], tile[r][c + 3]);
+              u.z = pack_bf16(tile[r][c + 4], tile[r][c + 5]); u.w = pack_bf16(tile[r][c + 6], tile[r][c + 7]);
+              *reinterpret_cast<uint4*>(dst) = u;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (n + c + k < p.N) dst[k] = __float2bfloat16_rn(tile[r][c + k]);
+            }
+          }
+        }
+      }
+    };
 
     const bool gate = (p.row_gate && row_ok) ? (p.row_gate[m] != 0) : true;
-    const float* rb = (p.row_bias && row_ok) ? p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias : nullptr;
-    const float* res = (p.residual && row_ok) ? p.residual + (long long)m * p.ld_residual : nullptr;
-    const float* res2 = (p.residual2 && row_ok) ? p.residual2 + (long long)m * p.ld_residual2 : nullptr;
     const bool do_ln = p.ln_gamma != nullptr;
     float s1 = 0.f, s2 = 0.f;
 
@@ -236,19 +318,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       float v[32], t[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.bias) { load32(p.bias + n, t);
+      if (p.bias) { load_vec(p.bias, n, t);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += t[j]; }
-      if (rb) { load32(rb + n, t);
+      if (p.row_bias) { stage_in(p.row_bias, p.ld_row_bias, p.row_bias_period, n, t);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += t[j]; }
       if (!gate) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f; }
-      if (res) { load32(res + n, t);
+      if (p.residual) { stage_in(p.residual, p.ld_residual, 0, n, t);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += t[j]; }
-      if (res2) { load32(res2 + n, t);
+      if (p.residual2) { stage_in(p.residual2, p.ld_residual2, 0, n, t);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += t[j]; }
       if (do_ln) {
@@ -256,30 +338,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); r[j] = __float_as_uint(v[j]); }
         tmem_st32(trow + c * 32, r);          // park the pre-norm row in TMEM for pass 2
       } else {
-        // no LayerNorm: finish right here
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f); }
-        if (p.post_add && row_ok) { load32(p.post_add + (long long)m * p.ld_post_add + n, t);
+        if (p.post_add) { stage_in(p.post_add, p.ld_post_add, 0, n, t);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += t[j]; }
-        if (row_ok) {
-          if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_out_f32 + n);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          if (p.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + (long long)m * p.ld_out_bf16 + n);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-              u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-              o[i] = u;
-            }
-          }
-        }
+        stage_out(n, v);
       }
     }
     if (do_ln) {
@@ -294,33 +359,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tmem_ld32(trow + c * 32, r);
         const int n = n0 + c * 32;
         float v[32], g[32], b[32];
-        load32(p.ln_gamma + n, g);
-        load32(p.ln_beta + n, b);
+        load_vec(p.ln_gamma, n, g);
+        load_vec(p.ln_beta, n, b);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           v[j] = fmaf((__uint_as_float(r[j]) - mean) * rstd, g[j], b[j]);
           if (p.relu) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.post_add && row_ok) { load32(p.post_add + (long long)m * p.ld_post_add + n, g);
+        if (p.post_add) { stage_in(p.post_add, p.ld_post_add, 0, n, g);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += g[j]; }
-        if (row_ok) {
-          if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * p.ld_out_f32 + n);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          if (p.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + (long long)m * p.ld_out_bf16 + n);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-              u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-              o[i] = u;
-            }
-          }
-        }
+        stage_out(n, v);
       }
     }
     tc_fence_before();
@@ -402,7 +451,7 @@ int launch_bn(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
     if (e != cudaSuccess) { set_error("tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
-  dim3 grid((a->M + BM - 1) / BM, a->N / BN);
+  dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN);
   linear_tc_kernel<BN><<<grid, kThreads, smem, s>>>(ma, mw, ep);
   count_launch();
   return check_launch("tc_linear(tcgen05)");
@@ -412,14 +461,8 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 }  // namespace
 
-bool linear_tc_supported(const tc_linear_args* a) {
-  if (a->a_dtype != TC_BF16 || a->w_dtype != TC_BF16) return false;
-  if (a->K % BK != 0 || a->K < BK) return false;
-  const int N = a->N;
-  if (!(N == 64 || N == 128 || (N % 256 == 0))) return false;
-  if (a->ln_gamma && N != 256) return false;
-  if (!al16(a->A) || !al16(a->W) || (a->lda * 2) % 16 != 0 || (a->ldw * 2) % 16 != 0) return false;
-  // epilogue uses 128-bit accesses on every row-wise operand
+static bool epilogue_vectorizable(const tc_linear_args* a) {
+  if (a->N % 32 != 0) return false;
   if (a->bias && !al16(a->bias)) return false;
   if (a->row_bias && (!al16(a->row_bias) || a->ld_row_bias % 4 != 0)) return false;
   if (a->residual && (!al16(a->residual) || a->ld_residual % 4 != 0)) return false;
@@ -428,6 +471,17 @@ bool linear_tc_supported(const tc_linear_args* a) {
   if (a->ln_gamma && (!al16(a->ln_gamma) || !al16(a->ln_beta))) return false;
   if (a->out_f32 && (!al16(a->out_f32) || a->ld_out_f32 % 4 != 0)) return false;
   if (a->out_bf16 && (!al16(a->out_bf16) || a->ld_out_bf16 % 8 != 0)) return false;
+  return true;
+}
+
+bool linear_tc_supported(const tc_linear_args* a) {
+  if (a->a_dtype != TC_BF16 || a->w_dtype != TC_BF16) return false;
+  if (a->K % BK != 0 || a->K < BK) return false;
+  const int N = a->N;
+  if (!(N <= 32 || N == 64 || N == 128 || (N % 256 == 0))) return false;
+  if (a->ln_gamma && N != 256) return false;
+  // TMA: 16-byte aligned base and row pitch for both operands
+  if (!al16(a->A) || !al16(a->W) || (a->lda * 2) % 16 != 0 || (a->ldw * 2) % 16 != 0) return false;
   return true;
 }
 
@@ -445,6 +499,8 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   ep.post_add = a->post_add; ep.ld_post_add = a->ld_post_add;
   ep.out_f32 = a->out_f32; ep.ld_out_f32 = a->ld_out_f32;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); ep.ld_out_bf16 = a->ld_out_bf16;
+  ep.vec = epilogue_vectorizable(a) ? 1 : 0;
+  if (a->N <= 32) return launch_bn<32>(a, ep, s);
   if (a->N == 64) return launch_bn<64>(a, ep, s);
   if (a->N == 128) return launch_bn<128>(a, ep, s);
   return launch_bn<256>(a, ep, s);
