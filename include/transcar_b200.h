@@ -151,8 +151,9 @@ TC_API int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream);
  *
  *   q [B, Lq, heads*D]  k, v [B, Lk, heads*D]   (dtype qkv_dtype; ld* = row stride in elements)
  *   out [B, Lq, heads*D] out_dtype
- *   geom (optional) [B, Lq, 8] fp32 = (cx, cy, fx, fy, rx, ry, radius, 0): centre / front / rear circle
- *         centres in metres and the clamped radius - produced by tc_radar_geometry
+ *   geom (optional) [B, Lq, 8] fp32 = (cx, cy, fx, fy, rx, ry, radius, thr): centre / front / rear circle
+ *         centres in metres, the clamped radius and thr = the smallest fp32 whose square root is >= radius
+ *         (sqrt(x) < radius  <=>  x < thr) - produced by tc_radar_geometry
  *   key_xy (with geom) [B, Lk, 2] fp32 radar x,y in metres (padding slots hold 500)
  *   row_any (optional) [B, Lq] uint8: 1 if the row has at least one allowed key.  Rows without any
  *         allowed key produce out = 0 (they skip attention in the reference: quirk Q6).

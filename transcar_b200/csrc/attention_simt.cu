@@ -200,8 +200,14 @@ __global__ void radar_geometry_kernel(const tc_radar_geometry_args a) {
   g[0] = cx; g[1] = cy;
   g[2] = __fadd_rn(cx, ox); g[3] = __fadd_rn(cy, oy);
   g[4] = __fsub_rn(cx, ox); g[5] = __fsub_rn(cy, oy);
-  g[6] = fminf(fmaxf(__fdiv_rn(len, 2.0f), a.r_lo), a.r_hi);
-  g[7] = 0.f;
+  const float radius = fminf(fmaxf(__fdiv_rn(len, 2.0f), a.r_lo), a.r_hi);
+  g[6] = radius;
+  // thr = smallest fp32 y with sqrt_rn(y) >= radius, so that  sqrt(x) < radius  <=>  x < thr  exactly (x >= 0).
+  // Lets the tensor-core attention kernel test squared distances without a square root per (query, key).
+  float thr = __fmul_rn(radius, radius);
+  for (int it = 0; it < 8 && thr > 0.f && __fsqrt_rn(thr) >= radius; ++it) thr = nextafterf(thr, 0.f);
+  for (int it = 0; it < 16 && __fsqrt_rn(thr) < radius; ++it) thr = nextafterf(thr, INFINITY);
+  g[7] = thr;
 }
 
 __global__ void __launch_bounds__(256) radar_mask_kernel(const float* __restrict__ geom, const float* __restrict__ key_xy,

@@ -1,6 +1,383 @@
-// K4 tensor-core path (tcgen05 + TMEM).  Placeholder until the kernel lands.
+// K4 tensor-core path: softmax(scale * Q K^T + mask) V for head dim 32, bf16 operands, fp32 accumulation.
+//
+// One CTA = 128 queries of one (sample, head); keys/values stream through a 2-stage TMA ring in 128-key tiles.
+//   S  = Q K^T   tcgen05.mma 128x128x16 (x2), both operands K-major SWIZZLE_64B, accumulator in TMEM cols [0,128)
+//   P  = online softmax of S: 4 warps, one query row per thread (tcgen05.ld 32x32b), radar distance mask evaluated
+//        in-kernel from per-query circle geometry (no sqrt: d < r  <=>  d^2 < thr(r), thr precomputed exactly),
+//        bf16 P written to shared memory in the K-major SWIZZLE_128B layout the next MMA expects
+//   O += P V     tcgen05.mma 128x32x16 (x8), A = P (shared memory), B = V tile used MN-major (SWIZZLE_64B) straight
+//        from its [keys, 32] row-major TMA image; accumulator in TMEM cols [128,160), rescaled in place
+//        (tcgen05.ld / st) when the running row maximum moves.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax/epilogue.
+// Two CTAs share an SM (2 x 256 TMEM columns), so one CTA's softmax overlaps the other's MMAs.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+
 #include "tc_common.cuh"
+#include "tc_sm100.cuh"
+
 namespace tc {
-bool attention_tc_supported(const tc_attention_args*) { return false; }
-int attention_tc_launch(const tc_attention_args*, cudaStream_t) { set_error("tc_attention_fwd: tensor-core path not built"); return TC_ERR_DTYPE; }
+namespace {
+
+constexpr int kBQ = 128, kBKV = 128, kD = 32;
+constexpr int kThreads = 192;
+constexpr uint32_t kTileBytes = kBKV * kD * 2;          // 8 KB: one Q / K / V tile
+constexpr uint32_t kPHalfBytes = kBQ * 64 * 2;          // 16 KB: P for 64 keys
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnTcParams {
+  int B, Lq, Lk, heads;
+  float scale_log2;                 // scale * log2(e)
+  const float* geom;                // [B, Lq, 8] or null
+  const float* key_xy;              // [B, Lk, 2]
+  __nv_bfloat16* out; long long ldo;
+  uint8_t* row_any;
+};
+
+// shared-memory carve-up (offsets from a 1024-aligned base)
+constexpr uint32_t kOffQ = 0;
+constexpr uint32_t kOffK = kOffQ + kTileBytes;                  // 2 stages
+constexpr uint32_t kOffV = kOffK + 2 * kTileBytes;              // 2 stages
+constexpr uint32_t kOffP = kOffV + 2 * kTileBytes;              // 2 halves x 16 KB  (offset 40 KB, 1024-aligned)
+constexpr uint32_t kOffKey = kOffP + 2 * kPHalfBytes;           // 2 stages x 3 x 128 floats
+constexpr uint32_t kOffBar = kOffKey + 2 * 3 * kBKV * 4;
+constexpr uint32_t kSmemUsed = kOffBar + 128;
+constexpr uint32_t kSmemBytes = 100 * 1024;                     // padded so that at most 2 CTAs fit on an SM
+
+template <bool kMask>
+__global__ void __launch_bounds__(kThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  // barriers: 0 q_full, 1-2 kv_full, 3-4 kv_empty, 5 s_full, 6 p_full, 7 o_done; then the TMEM slot
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t q_full = bar0, kv_full = bar0 + 8, kv_empty = bar0 + 24, s_full = bar0 + 40, p_full = bar0 + 48,
+                 o_done = bar0 + 56;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* key_geo = reinterpret_cast<float*>(smem + kOffKey);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
+  const int T = (p.Lk + kBKV - 1) / kBKV;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(kv_full, 1); mbar_init(kv_full + 8, 1);
+    mbar_init(kv_empty, 1); mbar_init(kv_empty + 8, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0 && T > 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sbase + kOffQ, &map_q, h * kD, q0, b, q_full);
+      for (int j = 0; j < T; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(kv_full + 8 * s, 2 * kTileBytes);
+        tma_load_3d(sbase + kOffK + s * kTileBytes, &map_k, h * kD, j * kBKV, b, kv_full + 8 * s);
+        tma_load_3d(sbase + kOffV + s * kTileBytes, &map_v, h * kD, j * kBKV, b, kv_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0 && T > 0) {
+      // kind::f16 descriptors: D=F32, A=B=BF16; S: M=128,N=128 (both K-major); O: M=128,N=32, B MN-major (bit 16)
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t dq = make_desc_sw64_kmajor(sbase + kOffQ);
+      mbar_wait(q_full, 0);
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      {
+        const uint64_t dk = make_desc_sw64_kmajor(sbase + kOffK);
+        umma_bf16(tmem_S, dq, dk, idesc_s, 0u);
+        umma_bf16(tmem_S, dq + 2, dk + 2, idesc_s, 1u);
+        umma_commit(s_full);
+      }
+      for (int j = 0; j < T; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);                 // P(j) in smem, O rescaled, S(j) consumed
+        tc_fence_after();
+#pragma unroll
+        for (int k16 = 0; k16 < kBKV / 16; ++k16) {
+          const uint64_t dp = make_desc_sw128(sbase + kOffP + (k16 >> 2) * kPHalfBytes) + 2 * (k16 & 3);
+          const uint64_t dv = make_desc_sw64_mnmajor(sbase + kOffV + s * kTileBytes + k16 * 1024, 8192);
+          umma_bf16(tmem_O, dp, dv, idesc_o, (j | k16) ? 1u : 0u);
+        }
+        umma_commit(kv_empty + 8 * s);            // K/V stage s may be refilled
+        umma_commit(o_done);                      // O(j) accumulated, P buffer free
+        if (j + 1 < T) {
+          const int s1 = (j + 1) & 1;
+          mbar_wait(kv_full + 8 * s1, ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint64_t dk = make_desc_sw64_kmajor(sbase + kOffK + s1 * kTileBytes);
+          umma_bf16(tmem_S, dq, dk, idesc_s, 0u);
+          umma_bf16(tmem_S, dq + 2, dk + 2, idesc_s, 1u);
+          umma_commit(s_full);
+        }
+      }
+    }
+  } else {
+    // ===== softmax + epilogue: warps 2..5, TMEM lane quadrant = warp % 4, one query row per thread =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;           // row inside the tile
+    const int q = q0 + row;
+    const bool row_ok = q < p.Lq;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int tid128 = threadIdx.x - 64;
+
+    Circle cc, cf, cr;
+    float thr = 0.f;
+    if (kMask) {
+      cc = make_circle(0.f, 0.f); cf = cc; cr = cc;
+      if (row_ok) {
+        const float* g = p.geom + ((long long)b * p.Lq + q) * 8;
+        cc = make_circle(g[0], g[1]); cf = make_circle(g[2], g[3]); cr = make_circle(g[4], g[5]);
+        thr = g[7];
+      }
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < T; ++j) {
+      const int k0 = j * kBKV;
+      float* kx = key_geo + (j & 1) * 3 * kBKV;
+      float* ky = kx + kBKV;
+      float* kn = ky + kBKV;
+      if (kMask) {
+        const int key = k0 + tid128;
+        float x = 0.f, y = 0.f;
+        if (key < p.Lk) {
+          x = p.key_xy[((long long)b * p.Lk + key) * 2 + 0];
+          y = p.key_xy[((long long)b * p.Lk + key) * 2 + 1];
+        }
+        kx[tid128] = x; ky[tid128] = y; kn[tid128] = key_norm(x, y);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+
+      // ---- pass A: scaled, masked row maximum; remember which keys are allowed -------------------------
+      uint32_t allow[4];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, r);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kk = c * 32 + i;
+          bool ok = (k0 + kk) < p.Lk;
+          if (kMask) {
+            // cdist(mm route) < radius, evaluated on squared distances: acc < thr  (thr: smallest float whose sqrt >= r)
+            const float x = kx[kk], y = ky[kk], n = kn[kk];
+            const float dc = __fmaf_rn(1.0f, n, __fmaf_rn(cc.nrm, 1.0f, __fmaf_rn(cc.m2y, y, __fmul_rn(cc.m2x, x))));
+            const float df = __fmaf_rn(1.0f, n, __fmaf_rn(cf.nrm, 1.0f, __fmaf_rn(cf.m2y, y, __fmul_rn(cf.m2x, x))));
+            const float dr = __fmaf_rn(1.0f, n, __fmaf_rn(cr.nrm, 1.0f, __fmaf_rn(cr.m2y, y, __fmul_rn(cr.m2x, x))));
+            ok = ok && ((dc < thr) | (df < thr) | (dr < thr));
+          }
+          if (ok) {
+            bits |= 1u << i;
+            mx = fmaxf(mx, __uint_as_float(r[i]) * p.scale_log2);
+          }
+        }
+        allow[c] = bits;
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = (m_new == -INFINITY) ? 1.0f : exp2f(m_run - m_new);      // m_run = -inf -> 0
+      l_run *= corr;
+
+      // ---- O rescale (needs PV(j-1) retired; also frees the P buffer) ------------------------------------
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, corr != 1.0f)) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_off, o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+          tmem_st32(tmem_O + lane_off, o);
+        }
+      }
+
+      // ---- pass B: probabilities -> bf16 P in shared memory (K-major, 128B swizzle) ----------------------
+      uint8_t* prow = smem + kOffP + row * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, r);
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
+          pv[i] = ((allow[c] >> i) & 1u) ? e : 0.f;
+          l_run += pv[i];
+        }
+        uint8_t* half = prow + (c >> 1) * kPHalfBytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {          // 4 x 16-byte chunks = 32 keys
+          uint4 u;
+          u.x = pack_bf16(pv[8 * g + 0], pv[8 * g + 1]); u.y = pack_bf16(pv[8 * g + 2], pv[8 * g + 3]);
+          u.z = pack_bf16(pv[8 * g + 4], pv[8 * g + 5]); u.w = pack_bf16(pv[8 * g + 6], pv[8 * g + 7]);
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(half + ((chunk ^ (row & 7)) << 4)) = u;
+        }
+      }
+      m_run = m_new;
+      fence_proxy_async_smem();                // generic-proxy smem writes -> visible to the MMA (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> bf16 ---------------------------------------------------------------------------
+    float o[32];
+    if (T > 0) {
+      mbar_wait(o_done, (T - 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem_O + lane_off, r);
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = l_run > 0.f ? __uint_as_float(r[i]) * inv : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    }
+    if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * p.Lq + q) * p.ldo + h * kD);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        u.x = pack_bf16(o[8 * g + 0], o[8 * g + 1]); u.y = pack_bf16(o[8 * g + 2], o[8 * g + 3]);
+        u.z = pack_bf16(o[8 * g + 4], o[8 * g + 5]); u.w = pack_bf16(o[8 * g + 6], o[8 * g + 7]);
+        dst[g] = u;
+      }
+      if (p.row_any && h == 0) p.row_any[(long long)b * p.Lq + q] = l_run > 0.f ? 1 : 0;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---- host: 3-D tensor maps [E, L, B] with a 32 x 128 x 1 box, 64-byte swizzle ------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn3() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct Key3 {
+  const void* ptr; long long ld, bs; int E, L, B;
+  bool operator==(const Key3& o) const { return ptr == o.ptr && ld == o.ld && bs == o.bs && E == o.E && L == o.L && B == o.B; }
+};
+struct Key3Hash {
+  size_t operator()(const Key3& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.bs; h = h * 1000003u ^ (size_t)k.E;
+    h = h * 1000003u ^ (size_t)k.L;
+    return h * 1000003u ^ (size_t)k.B;
+  }
+};
+
+bool get_map3(const void* ptr, long long ld, long long bs, int E, int L, int B, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<Key3, CUtensorMap, Key3Hash> cache;
+  Key3 key{ptr, ld, bs, E, L, B};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn fn = encode_fn3();
+  if (!fn) { set_error("tc_attention_fwd: cuTensorMapEncodeTiled entry point not available"); return false; }
+  cuuint64_t dims[3] = {(cuuint64_t)E, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(B > 1 ? bs : (long long)L * ld) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kD, (cuuint32_t)kBKV, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("tc_attention_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
+  if (cache.size() > 1024) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return true;
+}
+
+}  // namespace
+
+bool attention_tc_supported(const tc_attention_args* a) {
+  static const bool disabled = getenv("TC_DISABLE_TC_ATTENTION") != nullptr;     // debugging / A-B measurements
+  if (disabled) return false;
+  if (a->qkv_dtype != TC_BF16 || a->out_dtype != TC_BF16) return false;
+  if (a->D != kD || a->Lk <= 0) return false;
+  const int E = a->heads * a->D;
+  (void)E;
+  // TMA: 16-byte aligned bases / pitches (checked by the caller), batch stride a multiple of 16 bytes
+  if ((a->q_batch_stride * 2) % 16 || (a->k_batch_stride * 2) % 16 || (a->v_batch_stride * 2) % 16) return false;
+  if ((a->ldo * 2) % 16 != 0) return false;
+  return true;
+}
+
+int attention_tc_launch(const tc_attention_args* a, cudaStream_t s) {
+  const int E = a->heads * a->D;
+  CUtensorMap mq, mk, mv;
+  if (!get_map3(a->q, a->ldq, a->q_batch_stride, E, a->Lq, a->B, &mq)) return TC_ERR_SHAPE;
+  if (!get_map3(a->k, a->ldk, a->k_batch_stride, E, a->Lk, a->B, &mk)) return TC_ERR_SHAPE;
+  if (!get_map3(a->v, a->ldv, a->v_batch_stride, E, a->Lk, a->B, &mv)) return TC_ERR_SHAPE;
+  AttnTcParams p;
+  p.B = a->B; p.Lq = a->Lq; p.Lk = a->Lk; p.heads = a->heads;
+  p.scale_log2 = a->scale * kLog2e;
+  p.geom = a->geom; p.key_xy = a->key_xy;
+  p.out = static_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
+  p.row_any = a->row_any;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) { set_error("tc_attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  static_assert(kSmemUsed + 1024 <= kSmemBytes, "shared-memory carve-up exceeds the request");
+  dim3 grid((a->Lq + kBQ - 1) / kBQ, a->heads, a->B);
+  if (a->geom) attention_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mq, mk, mv, p);
+  else attention_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(mq, mk, mv, p);
+  count_launch();
+  return check_launch("tc_attention_fwd(tcgen05)");
+}
+
 }  // namespace tc

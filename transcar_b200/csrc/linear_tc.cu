@@ -13,10 +13,12 @@
 // DESIGN.md discusses why they are latency- rather than throughput-bound).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
 #include "tc_common.cuh"
+#include "tc_sm100.cuh"
 
 namespace tc {
 namespace {
@@ -25,7 +27,6 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kStages = 4;
 constexpr int kThreads = 192;
-constexpr uint32_t kSpinLimit = 1u << 22;
 
 struct EpiParams {
   int M, N, K;
@@ -42,103 +43,6 @@ struct EpiParams {
   int vec;        // 1: N % 32 == 0 and every row-wise operand is 16-byte aligned -> 128-bit epilogue accesses
 };
 
-// ---- PTX wrappers --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded spin: a protocol bug becomes a trap (launch error), never a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-#define TC_R32(a) a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15], \
-                  a[16], a[17], a[18], a[19], a[20], a[21], a[22], a[23], a[24], a[25], a[26], a[27], a[28], a[29], a[30], a[31]
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
-// start>>4 | LBO(=1, unused for swizzled K-major)<<16 | SBO(=1024 B between 8-row groups)>>4 <<32 | version 1<<46 |
-// layout SWIZZLE_128B (2) << 61.  The tile base must be 1024-byte aligned (base_offset = 0).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 // ---- epilogue math for one 32-column chunk of one row ------------------------------------------------
 __device__ __forceinline__ void load32(const float* p, float (&v)[32]) {
 #pragma unroll
@@ -148,7 +52,7 @@ __device__ __forceinline__ void load32(const float* p, float (&v)[32]) {
   }
 }
 
-template <int BN>
+template <int BN, bool kVec>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const EpiParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -156,7 +60,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kBBytes = BN * BK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic (not an integer round-trip) so the compiler keeps the shared address space: LDS/STS, not LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
   const uint32_t smem_base = smem_u32(smem);
@@ -225,7 +130,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     mbar_wait(accbar, 0);
     tc_fence_after();
     float (*tile)[33] = reinterpret_cast<float (*)[33]>(smem + (warp - 2) * 4352);
-    const bool vec = p.vec != 0;
+    constexpr bool vec = kVec;
 
     // coalesced [32 rows x 32 cols] fp32 tile -> this thread's row.  row r of the warp lives at base + rowoff(r).
     auto stage_in = [&](const float* base, long long ld, int period, int n, float (&t)[32]) {
@@ -439,7 +344,7 @@ bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CU
   return true;
 }
 
-template <int BN>
+template <int BN, bool kVec>
 int launch_bn(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
   CUtensorMap ma, mw;
   if (!get_map(a->A, a->lda, a->M, a->K, BM, &ma)) return TC_ERR_SHAPE;
@@ -447,12 +352,12 @@ int launch_bn(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
   constexpr size_t smem = (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<BN, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
   dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN);
-  linear_tc_kernel<BN><<<grid, kThreads, smem, s>>>(ma, mw, ep);
+  linear_tc_kernel<BN, kVec><<<grid, kThreads, smem, s>>>(ma, mw, ep);
   count_launch();
   return check_launch("tc_linear(tcgen05)");
 }
@@ -475,6 +380,8 @@ static bool epilogue_vectorizable(const tc_linear_args* a) {
 }
 
 bool linear_tc_supported(const tc_linear_args* a) {
+  static const bool disabled = getenv("TC_DISABLE_TC_LINEAR") != nullptr;        // debugging / A-B measurements
+  if (disabled) return false;
   if (a->a_dtype != TC_BF16 || a->w_dtype != TC_BF16) return false;
   if (a->K % BK != 0 || a->K < BK) return false;
   const int N = a->N;
@@ -499,11 +406,12 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   ep.post_add = a->post_add; ep.ld_post_add = a->ld_post_add;
   ep.out_f32 = a->out_f32; ep.ld_out_f32 = a->ld_out_f32;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); ep.ld_out_bf16 = a->ld_out_bf16;
-  ep.vec = epilogue_vectorizable(a) ? 1 : 0;
-  if (a->N <= 32) return launch_bn<32>(a, ep, s);
-  if (a->N == 64) return launch_bn<64>(a, ep, s);
-  if (a->N == 128) return launch_bn<128>(a, ep, s);
-  return launch_bn<256>(a, ep, s);
+  const bool vec = epilogue_vectorizable(a);
+  ep.vec = vec ? 1 : 0;
+  if (a->N <= 32) return vec ? launch_bn<32, true>(a, ep, s) : launch_bn<32, false>(a, ep, s);
+  if (a->N == 64) return vec ? launch_bn<64, true>(a, ep, s) : launch_bn<64, false>(a, ep, s);
+  if (a->N == 128) return vec ? launch_bn<128, true>(a, ep, s) : launch_bn<128, false>(a, ep, s);
+  return vec ? launch_bn<256, true>(a, ep, s) : launch_bn<256, false>(a, ep, s);
 }
 
 }  // namespace tc
