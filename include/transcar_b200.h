@@ -34,7 +34,7 @@ extern "C" {
 #define TC_API
 #endif
 
-#define TC_ABI_VERSION 1
+#define TC_ABI_VERSION 2
 #define TC_MAX_LEVELS 4
 #define TC_MAX_CAMS 8
 
@@ -157,7 +157,18 @@ TC_API int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream);
  *   key_xy (with geom) [B, Lk, 2] fp32 radar x,y in metres (padding slots hold 500)
  *   row_any (optional) [B, Lq] uint8: 1 if the row has at least one allowed key.  Rows without any
  *         allowed key produce out = 0 (they skip attention in the reference: quirk Q6).
+ *   algo  which kernel runs (tc_attention_algo).  The TransCAR mask admits ~0.1 % of the (query, radar point)
+ *         pairs, so TC_ATTN_AUTO sends masked calls to the sparse kernel (all 8 heads share one key scan and
+ *         only allowed pairs are computed) and mask-free calls (decoder self-attention) to the tcgen05 kernel;
+ *         an explicit value that the shape/dtype does not support is TC_ERR_SHAPE / TC_ERR_DTYPE.
  */
+typedef enum {
+  TC_ATTN_AUTO = 0,     /* masked + 8x32 heads -> TC_ATTN_SPARSE; bf16 dense -> TC_ATTN_TENSOR; else TC_ATTN_SIMT */
+  TC_ATTN_TENSOR = 1,   /* tcgen05/TMA dense-tile kernel (bf16 operands), mask evaluated per 128x128 tile in-kernel */
+  TC_ATTN_SIMT = 2,     /* CUDA-core dense-tile kernel (fp32 parity mode) */
+  TC_ATTN_SPARSE = 3    /* radar path: per-query key scan, only allowed (query, key) pairs are computed (needs geom) */
+} tc_attention_algo;
+
 typedef struct {
   const void* q; const void* k; const void* v;
   int64_t ldq, ldk, ldv;
@@ -169,6 +180,7 @@ typedef struct {
   const float* key_xy;
   void* out; int64_t ldo; int32_t out_dtype;
   uint8_t* row_any;
+  int32_t algo;                /* tc_attention_algo; TC_ATTN_AUTO (0) picks the fastest exact path */
 } tc_attention_args;
 TC_API int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream);
 

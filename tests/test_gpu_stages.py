@@ -312,8 +312,9 @@ def test_attention_dense(ops, mode, Lq, Lk):
         torch.testing.assert_close(out.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_attention_radar_mask_in_kernel(ops, mode):
+@pytest.mark.parametrize("mode,algo", [("fp32", "sparse"), ("fp32", "simt"), ("bf16", "sparse"), ("bf16", "tensor"),
+                                       ("bf16", "simt"), ("bf16", "auto")])
+def test_attention_radar_mask_in_kernel(ops, mode, algo):
     B, Q, R, heads, E = 2, 900, 1500, 8, 256
     radar_xy, centre, code = _geometry_inputs(B, Q, R, seed=23)
     geom = ops.radar_geometry(centre.view(B * Q, 3), code.view(B * Q, 10), synthetic.PC_RANGE, 1.0, 2.0, True)
@@ -323,7 +324,7 @@ def test_attention_radar_mask_in_kernel(ops, mode):
     if mode == "bf16":
         qbuf, kvbuf = qbuf.bfloat16(), kvbuf.bfloat16()
     out, row_any = ops.attention(qbuf, kvbuf[:, :, :E], kvbuf[:, :, E:], heads, geom=geom, key_xy=radar_xy,
-                                 want_row_any=True)
+                                 want_row_any=True, algo=algo)
     want = _oracle_mha_core(qbuf.float(), kvbuf[:, :, :E].float(), kvbuf[:, :, E:].float(), heads, blocked)
     any_allowed = (~blocked).any(-1)
     assert torch.equal(row_any.bool(), any_allowed)
@@ -331,6 +332,10 @@ def test_attention_radar_mask_in_kernel(ops, mode):
     assert (out[~any_allowed] == 0).all(), "rows without an allowed key must produce exact zeros (quirk Q6)"
     if mode == "fp32":
         torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+    elif algo == "tensor":
+        # dense-tile tcgen05 kernel: P is rounded to bf16 before P.V (both MMA operands must share one 16-bit format),
+        # which costs up to 2^-9 * sum|p v| on rows that attend to two or three keys with cancelling values
+        torch.testing.assert_close(out.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL * 6)
     else:
         torch.testing.assert_close(out.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
 

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libtranscar_b200.so")
 
 TC_F32, TC_BF16 = 0, 1
 TC_MAX_LEVELS, TC_MAX_CAMS = 4, 8
-ABI_VERSION = 1
+ABI_VERSION = 2
+TC_ATTN_AUTO, TC_ATTN_TENSOR, TC_ATTN_SIMT, TC_ATTN_SPARSE = 0, 1, 2, 3
 
 _vp, _i32, _i64, _f32, _u8p = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -59,7 +60,7 @@ class AttentionArgs(C.Structure):
                 ("scale", _f32),
                 ("geom", _vp), ("key_xy", _vp),
                 ("out", _vp), ("ldo", _i64), ("out_dtype", _i32),
-                ("row_any", _vp)]
+                ("row_any", _vp), ("algo", _i32)]
 
 
 class RadarGeometryArgs(C.Structure):

@@ -103,6 +103,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (lane == 0 && T > 0) {
       // kind::f16 descriptors: D=F32, A=B=BF16; S: M=128,N=128 (both K-major); O: M=128,N=32, B MN-major (bit 16)
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // (A and B must share one 16-bit format: an FP16 P against a BF16 V is rejected as an illegal instruction - measured.)
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t dq = make_desc_sw64_kmajor(sbase + kOffQ);
       mbar_wait(q_full, 0);

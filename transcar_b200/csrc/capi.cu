@@ -33,6 +33,8 @@ bool linear_tc_supported(const tc_linear_args* a);
 int linear_tc_launch(const tc_linear_args* a, cudaStream_t s);
 bool attention_tc_supported(const tc_attention_args* a);
 int attention_tc_launch(const tc_attention_args* a, cudaStream_t s);
+bool attention_sparse_supported(const tc_attention_args* a);
+int attention_sparse_launch(const tc_attention_args* a, cudaStream_t s);
 
 }  // namespace tc
 
@@ -98,8 +100,24 @@ extern "C" int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream) 
                  (a->ldo * eo) % 16 == 0 && (a->q_batch_stride * es) % 16 == 0 && (a->k_batch_stride * es) % 16 == 0 &&
                  (a->v_batch_stride * es) % 16 == 0,
              TC_ERR_ALIGN, "tc_attention_fwd: q/k/v/out rows must be 16-byte aligned");
+  TC_REQUIRE(a->algo >= TC_ATTN_AUTO && a->algo <= TC_ATTN_SPARSE, TC_ERR_SHAPE, "tc_attention_fwd: unknown algo %d", a->algo);
+  TC_REQUIRE(!a->key_xy || (reinterpret_cast<uintptr_t>(a->key_xy) & 7u) == 0, TC_ERR_ALIGN,
+             "tc_attention_fwd: key_xy must be 8-byte aligned");
   if (a->B == 0 || a->Lq == 0) return TC_OK;
   cudaStream_t s = as_stream(stream);
+  switch (a->algo) {
+    case TC_ATTN_SPARSE:
+      TC_REQUIRE(attention_sparse_supported(a), TC_ERR_SHAPE, "tc_attention_fwd: sparse path needs geom/key_xy and 8 heads x 32");
+      return attention_sparse_launch(a, s);
+    case TC_ATTN_TENSOR:
+      TC_REQUIRE(attention_tc_supported(a), TC_ERR_DTYPE, "tc_attention_fwd: tensor-core path needs bf16 q/k/v/out");
+      return attention_tc_launch(a, s);
+    case TC_ATTN_SIMT:
+      return attention_simt_launch(a, s);
+    default:
+      break;
+  }
+  if (attention_sparse_supported(a)) return attention_sparse_launch(a, s);
   if (attention_tc_supported(a)) return attention_tc_launch(a, s);
   return attention_simt_launch(a, s);
 }

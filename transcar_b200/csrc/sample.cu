@@ -2,20 +2,42 @@
 // sigmoid-weighted reduction).  See include/transcar_b200.h (tc_sample_fwd) for the contract and the
 // reference lines it replaces (detr3d_transformer.py:367-373, 381-422).
 //
-// Mapping: one warp per (sample, query).  Lane c < N projects the query through camera c's lidar2img
-// (matrices staged in shared memory, one sample per block row), a ballot yields the valid-camera set,
-// and the warp then walks the valid cameras only (~18 % of (query,cam) pairs are valid, 87 %
-// of queries see exactly one camera).  For a valid camera every lane owns 8 channels (bf16: one 128-bit
-// load per texel; fp32: two) of the channels-last feature vector, so a texel is one fully coalesced
-// 512-byte (bf16) or 2x512-byte (fp32) warp read; all 16 texel reads of a camera (4 levels x 4 corners)
-// are issued before the first is consumed.  HBM-bound: algorithmic bytes per valid pair =
-// 16 * C * sizeof(feat).
+// HBM-bound gather: algorithmic bytes per valid (query, camera) pair = 16 texels * C * sizeof(feat).
+// A random 8 KB gather is latency-bound unless ~100 KB per SM is in flight; a register-resident design (16 warps x
+// 16 x 128-bit loads, round-1 v1) spends half of its time with nothing in flight and reached 51 % of the HBM
+// roofline.  Here the texels are staged through shared memory with cp.async (LDGSTS: no registers held while in
+// flight) and the issue of a pair is decoupled from its consumption by a per-warp ring:
+//
+//   * one warp per (sample, query), persistent warps striding over the queries; the next query's reference
+//     point / logits / camera matrices are prefetched into registers one query ahead;
+//   * lane c < N projects the query through camera c's lidar2img (fp32, reference op order, bit-exact mask),
+//     a ballot yields the valid-camera set (~18 % of the pairs are valid);
+//   * for every valid pair and every 512-byte channel chunk, lanes 0..15 each own ONE texel (level = lane/4,
+//     corner = lane%4): they compute its index and bilinear*sigmoid weight and publish both in shared memory;
+//     then the whole warp issues 16 cp.async (one texel each, 16 bytes per lane = 512 coalesced bytes) into the
+//     warp's ring slot (8 KB) and commits them as one group.  A lane later reads back exactly the 16-byte pieces
+//     it copied itself, so the texel data needs no cross-lane synchronisation at all;
+//   * a warp keeps kSlots pairs in flight; it consumes the oldest slot (cp.async.wait_group, 16 conflict-free
+//     128-bit shared-memory reads per lane, fp32 FMA into the lane's 8 (bf16) or 4 (fp32) channels) only when the
+//     ring is full, and stores a query's channels once its last camera has been consumed.
+// (A cp.async.bulk per texel was measured first: UBLKCP takes uniform registers, so 16 per-lane copies turn into a
+// serialised ELECT/R2UR loop that cost a third of the kernel.)
+// 12 warps x 2 slots x 8 KB = 192 KB of shared memory per CTA, one CTA per SM.
 #include "tc_common.cuh"
 
 namespace tc {
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarps = 12;
+constexpr int kSlots = 2;
+constexpr int kTexels = 16;                     // 4 levels x 4 corners
+constexpr int kChunkBytes = 512;                // bytes of one texel handled per pass: 256 bf16 or 128 fp32 channels
+constexpr int kSlotBytes = kTexels * kChunkBytes;
+constexpr int kRingBytes = kWarps * kSlots * kSlotBytes;             // 196608
+constexpr int kWeightBytes = kWarps * kSlots * kTexels * 4;          // bilinear * sigmoid weight per texel
+constexpr int kIndexBytes = kWarps * kSlots * kTexels * 4;           // texel index per texel
+constexpr int kMetaBytes = kWarps * kSlots * 16;                     // row, channel offset, flags, pad
+constexpr int kSampleSmem = kRingBytes + kWeightBytes + kIndexBytes + kMetaBytes;
 
 struct SampleParams {
   const void* feat[TC_MAX_LEVELS];
@@ -36,186 +58,222 @@ __device__ __forceinline__ float unnormalize(float g, int size) {
   return (__fadd_rn(g, 1.0f) * static_cast<float>(size) - 1.0f) * 0.5f;
 }
 
-template <bool kBf16>
-struct Texel;
-
-template <>
-struct Texel<true> {                  // 8 bf16 channels per lane: channels [8*lane, 8*lane+8)
-  uint4 v;
-  __device__ __forceinline__ void load(const void* base, size_t texel, int C, int lane, int chunk) {
-    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + texel * C + chunk * 256 + lane * 8;
-    v = ldg_nc_u4(p);
-  }
-  // compiler-level fence: everything issued before stays before, consumers come after
-  __device__ __forceinline__ void pin() { asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)); }
-  __device__ __forceinline__ void fma_into(float (&acc)[8], float w) const {
-    acc[0] = fmaf(bf16_lo(v.x), w, acc[0]); acc[1] = fmaf(bf16_hi(v.x), w, acc[1]);
-    acc[2] = fmaf(bf16_lo(v.y), w, acc[2]); acc[3] = fmaf(bf16_hi(v.y), w, acc[3]);
-    acc[4] = fmaf(bf16_lo(v.z), w, acc[4]); acc[5] = fmaf(bf16_hi(v.z), w, acc[5]);
-    acc[6] = fmaf(bf16_lo(v.w), w, acc[6]); acc[7] = fmaf(bf16_hi(v.w), w, acc[7]);
-  }
-};
-
-template <>
-struct Texel<false> {                 // 8 fp32 channels per lane: [4*lane, +4) and [128 + 4*lane, +4)
-  uint4 a, b;
-  __device__ __forceinline__ void load(const void* base, size_t texel, int C, int lane, int chunk) {
-    const float* p = static_cast<const float*>(base) + texel * C + chunk * 256 + lane * 4;
-    a = ldg_nc_u4(p);
-    b = ldg_nc_u4(p + 128);
-  }
-  __device__ __forceinline__ void pin() {
-    asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w));
-  }
-  __device__ __forceinline__ void fma_into(float (&acc)[8], float w) const {
-    acc[0] = fmaf(__uint_as_float(a.x), w, acc[0]); acc[1] = fmaf(__uint_as_float(a.y), w, acc[1]);
-    acc[2] = fmaf(__uint_as_float(a.z), w, acc[2]); acc[3] = fmaf(__uint_as_float(a.w), w, acc[3]);
-    acc[4] = fmaf(__uint_as_float(b.x), w, acc[4]); acc[5] = fmaf(__uint_as_float(b.y), w, acc[5]);
-    acc[6] = fmaf(__uint_as_float(b.z), w, acc[6]); acc[7] = fmaf(__uint_as_float(b.w), w, acc[7]);
-  }
-};
-
-// Store 8 accumulated channels of one lane.
-template <bool kBf16In, bool kBf16Out>
-__device__ __forceinline__ void store_lane(void* out, size_t row, int C, int lane, int chunk, const float (&acc)[8]) {
-  if (kBf16In) {           // lane owns channels [8*lane, 8*lane+8)
-    if (kBf16Out) {
-      uint4 o;
-      o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-      o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + row * C + chunk * 256 + lane * 8) = o;
-    } else {
-      float4* p = reinterpret_cast<float4*>(static_cast<float*>(out) + row * C + chunk * 256 + lane * 8);
-      p[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      p[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-  } else {                 // lane owns channels [4*lane, +4) and [128+4*lane, +4)
-    if (kBf16Out) {
-      __nv_bfloat16* p = static_cast<__nv_bfloat16*>(out) + row * C + chunk * 256 + lane * 4;
-      uint2 lo, hi;
-      lo.x = pack_bf16(acc[0], acc[1]); lo.y = pack_bf16(acc[2], acc[3]);
-      hi.x = pack_bf16(acc[4], acc[5]); hi.y = pack_bf16(acc[6], acc[7]);
-      *reinterpret_cast<uint2*>(p) = lo;
-      *reinterpret_cast<uint2*>(p + 128) = hi;
-    } else {
-      float* p = static_cast<float*>(out) + row * C + chunk * 256 + lane * 4;
-      *reinterpret_cast<float4*>(p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(p + 128) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `n` of this thread's committed groups are still pending
+__device__ __forceinline__ void cp_async_wait(unsigned n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
   }
 }
 
-template <bool kBf16In, bool kBf16Out, int kLevels>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)   // minBlocks=4: ptxas then batches all 16 loads (checked in SASS)
-sample_kernel(const SampleParams p) {
-  constexpr int kGroup = kBf16In ? kLevels : kLevels / 2;
-  __shared__ float s_mat[TC_MAX_CAMS * 16];
-  const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < p.N * 16; i += blockDim.x) s_mat[i] = p.lidar2img[(size_t)b * p.N * 16 + i];
-  __syncthreads();
+// Per-query inputs, fetched one query ahead of their use.
+struct QueryIn {
+  float rx, ry, rz, logit;
+  float4 m0, m1, m2;          // rows 0..2 of this lane's camera matrix (lane < N)
+};
 
-  const int q = blockIdx.x * kWarpsPerBlock + warp;
-  if (q >= p.Q) return;
-  const size_t row = (size_t)b * p.Q + q;
-
-  // -- projection: lane c handles camera c (T:389-409), fp32, reference op order ------------------
-  const float rx = p.ref[row * 3 + 0], ry = p.ref[row * 3 + 1], rz = p.ref[row * 3 + 2];
-  const float px = __fadd_rn(__fmul_rn(rx, p.pc[3] - p.pc[0]), p.pc[0]);
-  const float py = __fadd_rn(__fmul_rn(ry, p.pc[4] - p.pc[1]), p.pc[1]);
-  const float pz = __fadd_rn(__fmul_rn(rz, p.pc[5] - p.pc[2]), p.pc[2]);
-  float gx = 0.f, gy = 0.f;
-  bool valid = false;
+__device__ __forceinline__ void fetch_query(const SampleParams& p, int task, int lane, QueryIn& in) {
+  const int b = task / p.Q;
+  const float* r = p.ref + (size_t)task * 3;
+  in.rx = __ldg(r); in.ry = __ldg(r + 1); in.rz = __ldg(r + 2);            // same address in every lane: broadcast
+  in.logit = (lane < p.N * 4) ? __ldg(p.logits + (size_t)task * (p.N * 4) + lane) : 0.f;
   if (lane < p.N) {
-    const float* m = s_mat + lane * 16;
-    // 4x4 . (px,py,pz,1) in the evaluation order of the batched K=4 SGEMM that torch.matmul dispatches to on
-    // sm_100 (found by tools/probe_matmul4.py: bit-identical on 21600/21600 outputs):
-    //   (m0*px (+) m1*py)  +  (m2*pz (+) m3*1)   with (+) = FMA
-    float cx = __fadd_rn(__fmaf_rn(m[1], py, __fmul_rn(m[0], px)), __fmaf_rn(m[3], 1.0f, __fmul_rn(m[2], pz)));
-    float cy = __fadd_rn(__fmaf_rn(m[5], py, __fmul_rn(m[4], px)), __fmaf_rn(m[7], 1.0f, __fmul_rn(m[6], pz)));
-    float cz = __fadd_rn(__fmaf_rn(m[9], py, __fmul_rn(m[8], px)), __fmaf_rn(m[11], 1.0f, __fmul_rn(m[10], pz)));
-    const float eps = 1e-5f;
-    valid = cz > eps;
-    const float zc = fmaxf(cz, eps);
-    // `x /= python_scalar` on a CUDA tensor is x * (1/scalar) in ATen (BinaryDivTrueKernel: cpu-scalar fast path),
-    // not a true division; tensor / tensor (the perspective divide) is IEEE division.
-    float u = __fmul_rn(__fdiv_rn(cx, zc), p.inv_w);
-    float v = __fmul_rn(__fdiv_rn(cy, zc), p.inv_h);
-    gx = __fmul_rn(__fadd_rn(u, -0.5f), 2.0f);
-    gy = __fmul_rn(__fadd_rn(v, -0.5f), 2.0f);
-    valid = valid && (gx > -1.0f) && (gx < 1.0f) && (gy > -1.0f) && (gy < 1.0f);
-    if (p.mask) p.mask[row * p.N + lane] = valid ? 1 : 0;
+    const float4* m = reinterpret_cast<const float4*>(p.lidar2img + ((size_t)b * p.N + lane) * 16);
+    in.m0 = __ldg(m); in.m1 = __ldg(m + 1); in.m2 = __ldg(m + 2);
   }
-  unsigned vset = __ballot_sync(0xffffffffu, valid);
+}
 
-  // -- sigmoid(attention logits): lane i < N*L holds weight i = cam*L + level ----------------------
-  float wgt = 0.f;
-  if (lane < p.N * kLevels) wgt = sigmoid_f32(p.logits[row * (size_t)(p.N * kLevels) + lane]);
+template <bool kBf16In, bool kBf16Out>
+__global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SampleParams p) {
+  constexpr int kPer = kBf16In ? 8 : 4;                 // channels per lane per chunk (16 bytes)
+  constexpr int kChunkCh = kBf16In ? 256 : 128;         // channels per 512-byte chunk
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* ring = smem + warp * kSlots * kSlotBytes + lane * 16;          // this lane's 16-byte column of the ring
+  float* wts = reinterpret_cast<float*>(smem + kRingBytes) + warp * kSlots * kTexels;
+  unsigned* tidx = reinterpret_cast<unsigned*>(smem + kRingBytes + kWeightBytes) + warp * kSlots * kTexels;
+  int* meta = reinterpret_cast<int*>(smem + kRingBytes + kWeightBytes + kIndexBytes) + warp * kSlots * 4;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
 
-  const int chunks = p.C >> 8;
-  for (int chunk = 0; chunk < chunks; ++chunk) {
-    float acc[8];
+  const int total = p.B * p.Q;
+  const int stride = gridDim.x * kWarps;
+  const int esz = kBf16In ? 2 : 4;
+  const int chunks = p.C / kChunkCh;
+  unsigned issued = 0, consumed = 0;                    // ring counters (warp-uniform)
+  float acc[kPer];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < kPer; ++i) acc[i] = 0.f;
 
-    unsigned todo = vset;
-    while (todo) {
-      const int cam = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const float x = __shfl_sync(0xffffffffu, gx, cam);
-      const float y = __shfl_sync(0xffffffffu, gy, cam);
-
-      // kGroup levels at a time: issue all 4*kGroup texel loads (16 independent 128-bit requests per
-      // lane for bf16, 2 levels x 8 for fp32), fence, then consume.
+  // ---- consume the oldest slot: wait for its 8 KB, weighted sum into acc, store on the pair that ends a (query, chunk)
+  auto consume = [&]() {
+    const unsigned slot = consumed % kSlots;
+    cp_async_wait(issued - consumed - 1);                                  // the oldest group has landed
+    const int4 mt = *reinterpret_cast<const int4*>(meta + slot * 4);        // row, channel offset, flags
+    if (mt.z & 1) {
 #pragma unroll
-      for (int l0 = 0; l0 < kLevels; l0 += kGroup) {
-        Texel<kBf16In> t[kGroup][4];
-        float cw[kGroup][4];
-        size_t addr[kGroup][4];
-        // phase 1: coordinates, corner weights and texel indices of the whole group (no loads yet)
+      for (int i = 0; i < kPer; ++i) acc[i] = 0.f;
+    }
+    const uint8_t* src = ring + slot * kSlotBytes;
+    const float4* w4 = reinterpret_cast<const float4*>(wts + slot * kTexels);
 #pragma unroll
-        for (int g = 0; g < kGroup; ++g) {
-          const int l = l0 + g;
-          const int H = p.H[l], W = p.W[l];
-          const float ix = unnormalize(x, W), iy = unnormalize(y, H);
-          const float fx0 = floorf(ix), fy0 = floorf(iy);
-          const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
-          const float wx1 = ix - fx0, wy1 = iy - fy0;                       // (ix - ix_nw), (iy - iy_nw)
-          const float wx0 = (fx0 + 1.0f) - ix, wy0 = (fy0 + 1.0f) - iy;     // (ix_se - ix), (iy_se - iy)
-          const float lw = __shfl_sync(0xffffffffu, wgt, cam * kLevels + l);
-          const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
-          const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
-          // zeros padding: out-of-range corners get weight 0 and a clamped (always legal) address
-          cw[g][0] = (vx0 & vy0) ? wx0 * wy0 * lw : 0.f;   // nw
-          cw[g][1] = (vx1 & vy0) ? wx1 * wy0 * lw : 0.f;   // ne
-          cw[g][2] = (vx0 & vy1) ? wx0 * wy1 * lw : 0.f;   // sw
-          cw[g][3] = (vx1 & vy1) ? wx1 * wy1 * lw : 0.f;   // se
-          const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
-          const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
-          const size_t plane = ((size_t)b * p.N + cam) * H;
-          addr[g][0] = (plane + cy0) * W + cx0;
-          addr[g][1] = (plane + cy0) * W + cx1;
-          addr[g][2] = (plane + cy1) * W + cx0;
-          addr[g][3] = (plane + cy1) * W + cx1;
+    for (int t4 = 0; t4 < kTexels / 4; ++t4) {
+      const float4 w = w4[t4];
+      const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + (t4 * 4 + j) * kChunkBytes);
+        if (kBf16In) {
+          acc[0] = fmaf(bf16_lo(v.x), ws[j], acc[0]); acc[1] = fmaf(bf16_hi(v.x), ws[j], acc[1]);
+          acc[2] = fmaf(bf16_lo(v.y), ws[j], acc[2]); acc[3] = fmaf(bf16_hi(v.y), ws[j], acc[3]);
+          acc[4 % kPer] = fmaf(bf16_lo(v.z), ws[j], acc[4 % kPer]); acc[5 % kPer] = fmaf(bf16_hi(v.z), ws[j], acc[5 % kPer]);
+          acc[6 % kPer] = fmaf(bf16_lo(v.w), ws[j], acc[6 % kPer]); acc[7 % kPer] = fmaf(bf16_hi(v.w), ws[j], acc[7 % kPer]);
+        } else {
+          acc[0] = fmaf(__uint_as_float(v.x), ws[j], acc[0]); acc[1] = fmaf(__uint_as_float(v.y), ws[j], acc[1]);
+          acc[2] = fmaf(__uint_as_float(v.z), ws[j], acc[2]); acc[3] = fmaf(__uint_as_float(v.w), ws[j], acc[3]);
         }
-        // phase 2: all loads back to back
-#pragma unroll
-        for (int g = 0; g < kGroup; ++g)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) t[g][c].load(p.feat[l0 + g], addr[g][c], p.C, lane, chunk);
-#pragma unroll
-        for (int g = 0; g < kGroup; ++g)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) t[g][c].pin();
-#pragma unroll
-        for (int g = 0; g < kGroup; ++g)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) t[g][c].fma_into(acc, cw[g][c]);
       }
     }
-    store_lane<kBf16In, kBf16Out>(p.out, row, p.C, lane, chunk, acc);
+    if (mt.z & 2) {
+      const size_t o = (size_t)mt.x * p.C + mt.y + lane * kPer;
+      if (kBf16Out) {
+        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + o;
+        if (kBf16In) {
+          uint4 u;
+          u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
+          u.z = pack_bf16(acc[4 % kPer], acc[5 % kPer]); u.w = pack_bf16(acc[6 % kPer], acc[7 % kPer]);
+          *reinterpret_cast<uint4*>(dst) = u;
+        } else {
+          uint2 u;
+          u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
+          *reinterpret_cast<uint2*>(dst) = u;
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (kBf16In) dst[1] = make_float4(acc[4 % kPer], acc[5 % kPer], acc[6 % kPer], acc[7 % kPer]);
+      }
+    }
+    ++consumed;
+    __syncwarp();                      // every lane has read the slot's weights / meta before they are overwritten
+  };
+
+  int task = blockIdx.x * kWarps + warp;
+  QueryIn cur, nxt;
+  if (task < total) fetch_query(p, task, lane, cur);
+  nxt = cur;
+
+  for (; task < total; task += stride, cur = nxt) {
+    const int b = task / p.Q;
+
+    // -- projection: lane c handles camera c (T:389-409), fp32, reference op order ------------------
+    const float px = __fadd_rn(__fmul_rn(cur.rx, p.pc[3] - p.pc[0]), p.pc[0]);
+    const float py = __fadd_rn(__fmul_rn(cur.ry, p.pc[4] - p.pc[1]), p.pc[1]);
+    const float pz = __fadd_rn(__fmul_rn(cur.rz, p.pc[5] - p.pc[2]), p.pc[2]);
+    float gx = 0.f, gy = 0.f;
+    bool valid = false;
+    if (lane < p.N) {
+      // 4x4 . (px,py,pz,1) in the evaluation order of the batched K=4 SGEMM that torch.matmul dispatches to on
+      // sm_100 (found by tools/probe_matmul4.py: bit-identical on 21600/21600 outputs):
+      //   (m0*px (+) m1*py)  +  (m2*pz (+) m3*1)   with (+) = FMA
+      const float4 m0 = cur.m0, m1 = cur.m1, m2 = cur.m2;
+      float cx = __fadd_rn(__fmaf_rn(m0.y, py, __fmul_rn(m0.x, px)), __fmaf_rn(m0.w, 1.0f, __fmul_rn(m0.z, pz)));
+      float cy = __fadd_rn(__fmaf_rn(m1.y, py, __fmul_rn(m1.x, px)), __fmaf_rn(m1.w, 1.0f, __fmul_rn(m1.z, pz)));
+      float cz = __fadd_rn(__fmaf_rn(m2.y, py, __fmul_rn(m2.x, px)), __fmaf_rn(m2.w, 1.0f, __fmul_rn(m2.z, pz)));
+      const float eps = 1e-5f;
+      valid = cz > eps;
+      const float zc = fmaxf(cz, eps);
+      // `x /= python_scalar` on a CUDA tensor is x * (1/scalar) in ATen (BinaryDivTrueKernel: cpu-scalar fast path),
+      // not a true division; tensor / tensor (the perspective divide) is IEEE division.
+      float u = __fmul_rn(__fdiv_rn(cx, zc), p.inv_w);
+      float v = __fmul_rn(__fdiv_rn(cy, zc), p.inv_h);
+      gx = __fmul_rn(__fadd_rn(u, -0.5f), 2.0f);
+      gy = __fmul_rn(__fadd_rn(v, -0.5f), 2.0f);
+      valid = valid && (gx > -1.0f) && (gx < 1.0f) && (gy > -1.0f) && (gy < 1.0f);
+      if (p.mask) p.mask[(size_t)task * p.N + lane] = valid ? 1 : 0;
+    }
+    const unsigned vset = __ballot_sync(0xffffffffu, valid);
+
+    // -- sigmoid(attention logits): lane i < N*4 holds weight i = cam*4 + level ----------------------
+    const float wgt = (lane < p.N * 4) ? sigmoid_f32(cur.logit) : 0.f;
+
+    // -- next query's inputs: issued now, consumed in the next iteration ------------------------------
+    if (task + stride < total) fetch_query(p, task + stride, lane, nxt);
+
+    if (vset == 0) {                                    // no camera sees the point: the masked sum is exactly 0
+      for (int c = lane * kPer; c < p.C; c += 32 * kPer) {
+        const size_t o = (size_t)task * p.C + c;
+        if (kBf16Out) {
+          if (kPer == 8) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o) = make_uint4(0, 0, 0, 0);
+          else *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + o) = make_uint2(0, 0);
+        } else {
+          float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
+          dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kPer == 8) dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      continue;
+    }
+
+    const int level = (lane >> 2) & 3, corner = lane & 3;
+    const int H = p.H[level], W = p.W[level];
+    const int last_cam = 31 - __clz(vset);
+    for (int chunk = 0; chunk < chunks; ++chunk) {
+      unsigned todo = vset;
+      bool first = true;
+      while (todo) {
+        const int cam = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if (issued - consumed == kSlots) consume();
+        // ---- issue: lanes 0..15 each own one texel of this (query, camera)
+        const float x = __shfl_sync(0xffffffffu, gx, cam);
+        const float y = __shfl_sync(0xffffffffu, gy, cam);
+        const float lw = __shfl_sync(0xffffffffu, wgt, cam * 4 + level);
+        const float ix = unnormalize(x, W), iy = unnormalize(y, H);
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int xi = (int)fx0 + (corner & 1), yi = (int)fy0 + (corner >> 1);      // nw, ne, sw, se
+        // ATen corner weights: (ix_se - ix) / (ix - ix_nw) and likewise in y
+        const float wx = (corner & 1) ? ix - fx0 : (fx0 + 1.0f) - ix;
+        const float wy = (corner >> 1) ? iy - fy0 : (fy0 + 1.0f) - iy;
+        const bool inside = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H);
+        // zeros padding: out-of-range corners get weight 0 and a clamped (always legal) address
+        const float w = inside ? wx * wy * lw : 0.f;
+        const int cxi = min(max(xi, 0), W - 1), cyi = min(max(yi, 0), H - 1);
+        const unsigned texel = (unsigned)((((size_t)b * p.N + cam) * H + cyi) * W + cxi);
+        const unsigned slot = issued % kSlots;
+        if (lane < kTexels) {
+          wts[slot * kTexels + lane] = w;
+          tidx[slot * kTexels + lane] = texel;
+        }
+        if (lane == 0)
+          *reinterpret_cast<int4*>(meta + slot * 4) =
+              make_int4(task, chunk * kChunkCh, (first ? 1 : 0) | (cam == last_cam ? 2 : 0), 0);
+        __syncwarp();
+        // ---- all lanes: 16 x (512 coalesced bytes global -> this lane's ring column)
+        const size_t row_bytes = (size_t)p.C * esz;
+        const size_t lane_off = (size_t)chunk * kChunkBytes + lane * 16;
+        const uint32_t dst = ring_u32 + slot * kSlotBytes;
+#pragma unroll
+        for (int t4 = 0; t4 < kTexels / 4; ++t4) {
+          const uint4 ti = *reinterpret_cast<const uint4*>(tidx + slot * kTexels + t4 * 4);
+          const uint8_t* base = static_cast<const uint8_t*>(p.feat[t4]) + lane_off;
+          cp_async16(dst + (t4 * 4 + 0) * kChunkBytes, base + ti.x * row_bytes);
+          cp_async16(dst + (t4 * 4 + 1) * kChunkBytes, base + ti.y * row_bytes);
+          cp_async16(dst + (t4 * 4 + 2) * kChunkBytes, base + ti.z * row_bytes);
+          cp_async16(dst + (t4 * 4 + 3) * kChunkBytes, base + ti.w * row_bytes);
+        }
+        cp_async_commit();
+        ++issued;
+        first = false;
+      }
+    }
   }
+  while (consumed != issued) consume();
 }
 
 // ---- NCHW fp32 -> NHWC (fp32|bf16) tiled transpose ------------------------------------------------
@@ -254,7 +312,8 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   TC_REQUIRE(a->N >= 1 && a->N <= TC_MAX_CAMS && a->N * a->num_levels <= 32, TC_ERR_SHAPE,
              "tc_sample_fwd: num cams %d unsupported", a->N);
   TC_REQUIRE(a->C > 0 && a->C % 256 == 0, TC_ERR_SHAPE, "tc_sample_fwd: C must be a multiple of 256 (got %d)", a->C);
-  TC_REQUIRE(a->B >= 0 && a->Q >= 0 && a->B <= 65535, TC_ERR_SHAPE, "tc_sample_fwd: bad B/Q");
+  TC_REQUIRE(a->B >= 0 && a->Q >= 0 && (long long)a->B * a->Q < (1ll << 30), TC_ERR_SHAPE, "tc_sample_fwd: bad B/Q");
+  TC_REQUIRE(aligned16(a->lidar2img), TC_ERR_ALIGN, "tc_sample_fwd: lidar2img must be 16-byte aligned");
   TC_REQUIRE(a->feat_dtype == TC_F32 || a->feat_dtype == TC_BF16, TC_ERR_DTYPE, "tc_sample_fwd: bad feat dtype");
   TC_REQUIRE(a->out_dtype == TC_F32 || a->out_dtype == TC_BF16, TC_ERR_DTYPE, "tc_sample_fwd: bad out dtype");
   TC_REQUIRE(aligned16(a->out), TC_ERR_ALIGN, "tc_sample_fwd: out must be 16-byte aligned");
@@ -271,14 +330,31 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   for (int i = 0; i < 6; ++i) p.pc[i] = a->pc_range[i];
   p.inv_w = 1.0f / a->img_w; p.inv_h = 1.0f / a->img_h;
   p.out = a->out; p.mask = a->mask;
-  dim3 grid((a->Q + kWarpsPerBlock - 1) / kWarpsPerBlock, a->B);
-  dim3 block(kWarpsPerBlock * 32);
+  // persistent warps, one CTA per SM (192 KB ring); warp w handles queries w, w + W, ...
+  static int sm_count = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    sm_count = n;
+    cudaError_t e = cudaFuncSetAttribute(sample_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sample_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sample_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sample_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem);
+    if (e != cudaSuccess) { set_error("tc_sample_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  const long long total = (long long)a->B * a->Q;
+  const long long ctas = (total + kWarps - 1) / kWarps;
+  dim3 grid((unsigned)(ctas < sm_count ? ctas : sm_count));
+  dim3 block(kWarps * 32);
   cudaStream_t s = as_stream(stream);
   const bool bi = a->feat_dtype == TC_BF16, bo = a->out_dtype == TC_BF16;
-  if (bi && bo) sample_kernel<true, true, 4><<<grid, block, 0, s>>>(p);
-  else if (bi) sample_kernel<true, false, 4><<<grid, block, 0, s>>>(p);
-  else if (bo) sample_kernel<false, true, 4><<<grid, block, 0, s>>>(p);
-  else sample_kernel<false, false, 4><<<grid, block, 0, s>>>(p);
+  if (bi && bo) sample_kernel<true, true><<<grid, block, kSampleSmem, s>>>(p);
+  else if (bi) sample_kernel<true, false><<<grid, block, kSampleSmem, s>>>(p);
+  else if (bo) sample_kernel<false, true><<<grid, block, kSampleSmem, s>>>(p);
+  else sample_kernel<false, false><<<grid, block, kSampleSmem, s>>>(p);
   count_launch();
   return check_launch("tc_sample_fwd");
 }

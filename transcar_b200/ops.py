@@ -179,7 +179,11 @@ def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, wa
 
 
 # --------------------------------------------------------------------------------------- K4
-def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_row_any=False, scale=None, out=None):
+ATTN_ALGOS = {"auto": _lib.TC_ATTN_AUTO, "tensor": _lib.TC_ATTN_TENSOR, "simt": _lib.TC_ATTN_SIMT, "sparse": _lib.TC_ATTN_SPARSE}
+
+
+def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_row_any=False, scale=None, out=None,
+              algo="auto"):
     """q [B,Lq,E], k/v [B,Lk,E] (views with a row stride are fine) -> out [B,Lq,E], row_any [B,Lq] or None."""
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -207,6 +211,7 @@ def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_ro
     row_any = torch.empty((B, Lq), device=q.device, dtype=torch.uint8) if want_row_any else None
     a.out, a.ldo, a.out_dtype = out.data_ptr(), out.stride(1), _DT[out.dtype]
     a.row_any = _ptr(row_any)
+    a.algo = ATTN_ALGOS[algo]
     _lib.check(lib.tc_attention_fwd(C.byref(a), _stream()), "attention")
     return out, row_any
 
