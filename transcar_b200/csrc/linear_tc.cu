@@ -1,16 +1,18 @@
 // K3 tensor-core path: Y = epilogue(A[M,K] * W[N,K]^T) with bf16 operands, fp32 accumulation in TMEM.
 //
-//   * operands: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a 4-stage shared-memory ring,
+// The GEMMs of this path are small (M = B*900 rows, N <= 1536, K <= 512): one 128 x 64 output tile per CTA keeps
+// all 148 SMs busy (2-3 resident CTAs each) and makes the per-thread epilogue short.
+//   * operands: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a 4-stage shared-memory ring (24 KB per stage),
 //     full/empty mbarriers; both operands are K-major (nn.Linear keeps W as [N,K]).
-//   * math: tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16 (BN = 64/128/256), issued by one thread;
-//     accumulator = 128 lanes x BN fp32 columns of tensor memory.
-//   * epilogue: 4 warps, one accumulator row per thread (tcgen05.ld 32x32b): bias / per-query row bias /
-//     row gate / two residuals / LayerNorm over the full row (BN = N = 256: statistics are thread-local, the
-//     pre-norm row is parked back in TMEM with tcgen05.st between the two passes) / ReLU / post-add, then fp32
-//     and/or bf16 stores.  No intermediate ever goes to HBM.
+//   * math: tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x 64 x 16, issued by one thread; accumulator = 128 lanes x
+//     64 fp32 columns of tensor memory.
+//   * the input-side epilogue terms (bias, per-query row bias, residuals) do not depend on the product, so the four
+//     epilogue warps load them WHILE the operands are in flight, write their sum into the accumulator's tensor
+//     memory (tcgen05.st) and the MMAs then accumulate on top of it: no side-input latency after the last MMA.
+//   * output side: one accumulator row per thread (tcgen05.ld 32x32b): LayerNorm / ReLU / post-add, 256-bit row
+//     stores.  LayerNorm needs the whole row (N = 64, 128 or 256): the 1, 2 or 4 CTAs that share a row block form
+//     a thread-block cluster and exchange per-row (sum, sum of squares) through distributed shared memory.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
-// One 128 x BN output tile per CTA (the GEMMs of this path are small: M = B*900 rows, N <= 1536, K <= 512;
-// DESIGN.md discusses why they are latency- rather than throughput-bound).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -24,9 +26,19 @@ namespace tc {
 namespace {
 
 constexpr int BM = 128;
+constexpr int BN = 64;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kStages = 4;
 constexpr int kThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 2;
+constexpr uint32_t kBBytes = BN * BK * 2;
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+// after the ring: barriers (full, empty, acc, init) + tmem slot, column vectors (bias, gamma, beta), LN partials
+constexpr uint32_t kOffBars = kStages * kStageBytes;
+constexpr uint32_t kOffVec = kOffBars + 128;
+constexpr uint32_t kOffPart = kOffVec + 3 * BN * 4;
+constexpr uint32_t kSmemUsed = kOffPart + BM * 8;
+constexpr size_t kSmemBytes = kSmemUsed + 1024;          // + alignment slack
 
 struct EpiParams {
   int M, N, K;
@@ -40,45 +52,98 @@ struct EpiParams {
   const float* post_add; long long ld_post_add;
   float* out_f32; long long ld_out_f32;
   __nv_bfloat16* out_bf16; long long ld_out_bf16;
-  int vec;        // 1: N % 32 == 0 and every row-wise operand is 16-byte aligned -> 128-bit epilogue accesses
+  int vec;        // 1: every row-wise operand is 32-byte aligned with a 32-byte multiple pitch -> 256-bit accesses
+  int has_init;   // bias / row_bias / residual(s) are folded into the accumulator before the first MMA
 };
 
-// ---- epilogue math for one 32-column chunk of one row ------------------------------------------------
-__device__ __forceinline__ void load32(const float* p, float (&v)[32]) {
+// ---- row-per-thread global access: 32 consecutive floats of one row ---------------------------------
+__device__ __forceinline__ void ld256(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st256u(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// v[j] += row[j], j < 32 (ncols valid columns)
+__device__ __forceinline__ void add_row32(const float* row, int ncols, bool vec, float (&v)[32]) {
+  if (vec && ncols >= 32) {
+    float t[32];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
-    v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    for (int i = 0; i < 4; ++i) ld256(row + 8 * i, t + 8 * i);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) v[j] += row[j];
   }
 }
 
-template <int BN, bool kVec>
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote) : "memory");
+  return v;
+}
+
+template <bool kLN>
+__global__ void __launch_bounds__(kThreads, 2)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const EpiParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A 16 KB][B BN*128 B] then barriers
-  constexpr uint32_t kABytes = BM * BK * 2;
-  constexpr uint32_t kBBytes = BN * BK * 2;
-  constexpr uint32_t kStageBytes = kABytes + kBBytes;
   // pointer arithmetic (not an integer round-trip) so the compiler keeps the shared address space: LDS/STS, not LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + kOffVec);
+  float* s_gamma = s_bias + BN;
+  float* s_beta = s_gamma + BN;
+  float2* s_part = reinterpret_cast<float2*>(smem + kOffPart);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), accbar = smem_u32(bars + 2 * kStages);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), accbar = smem_u32(bars + 2 * kStages),
+                 initbar = smem_u32(bars + 2 * kStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int num_kb = p.K / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(accbar, 1);
+    mbar_init(initbar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {          // column vectors of this tile (zero beyond N)
+    const int j = threadIdx.x - 64, n = n0 + j;
+    s_bias[j] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+    s_gamma[j] = (kLN && n < p.N) ? p.ln_gamma[n] : 0.f;
+    s_beta[j] = (kLN && n < p.N) ? p.ln_beta[n] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -97,12 +162,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tma_load_2d(a_dst + kABytes, &map_w, kb * BK, n0, full0 + 8 * s);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       // kind::f16 instruction descriptor: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), K-major A and B,
       // N>>3 at bit 17, M>>4 at bit 24
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      if (p.has_init) {                            // accumulator pre-loaded with bias + residuals by the epilogue warps
+        mbar_wait(initbar, 0);
+        tc_fence_after();
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -112,172 +182,150 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + kABytes);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)          // +32 bytes (2 x 16 B) per UMMA_K step inside the 128 B row
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (p.has_init | kb | k) ? 1u : 0u);
         umma_commit(empty0 + 8 * s);               // frees the smem slot once these MMAs retire
       }
       umma_commit(accbar);                         // accumulator complete
     }
+    __syncwarp();
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
-    // Math is one accumulator row per thread (tcgen05.ld 32x32b); every global read/write of a row-major
-    // operand goes through a per-warp 32x32 shared-memory tile so that each warp instruction touches whole
-    // 128-byte row segments (the pipeline stages are free once the accumulator barrier has fired).
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4, one accumulator row per thread =====
     const int quad = warp & 3;
-    const int row0 = m0 + quad * 32;            // first row of this warp
-    const int m = row0 + lane;
+    const int row = quad * 32 + lane;
+    const int m = m0 + row;
     const bool row_ok = m < p.M;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool vec = p.vec != 0;
+    const int ncols = min(BN, p.N - n0);
+    const bool gate = (p.row_gate && row_ok) ? (p.row_gate[m] != 0) : true;
+
+    // input-side terms of columns [c*32, c*32+32): (gate ? bias + row_bias : 0) + residual + residual2
+    auto side_terms = [&](int c, bool with_gated, float (&v)[32]) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      if (!row_ok) return;
+      const int nc = ncols - c * 32;
+      if (with_gated) {
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = s_bias[c * 32 + j];
+        }
+        if (p.row_bias) add_row32(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n0 + c * 32, nc, vec, v);
+      }
+      if (p.residual) add_row32(p.residual + (long long)m * p.ld_residual + n0 + c * 32, nc, vec, v);
+      if (p.residual2) add_row32(p.residual2 + (long long)m * p.ld_residual2 + n0 + c * 32, nc, vec, v);
+    };
+
+    if (p.has_init) {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        uint32_t r[32];
+        side_terms(c, gate, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+        tmem_st32(trow + c * 32, r);
+      }
+      tc_fence_before();
+      mbar_arrive(initbar);
+    }
+
     mbar_wait(accbar, 0);
     tc_fence_after();
-    float (*tile)[33] = reinterpret_cast<float (*)[33]>(smem + (warp - 2) * 4352);
-    constexpr bool vec = kVec;
 
-    // coalesced [32 rows x 32 cols] fp32 tile -> this thread's row.  row r of the warp lives at base + rowoff(r).
-    auto stage_in = [&](const float* base, long long ld, int period, int n, float (&t)[32]) {
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + (lane >> 3), c = (lane & 7) * 4;
-        const int gm = row0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gm < p.M) {
-          const float* src = base + (long long)(period > 0 ? gm % period : gm) * ld + n + c;
-          if (vec) {
-            v = *reinterpret_cast<const float4*>(src);
-          } else {
-            if (n + c + 0 < p.N) v.x = src[0];
-            if (n + c + 1 < p.N) v.y = src[1];
-            if (n + c + 2 < p.N) v.z = src[2];
-            if (n + c + 3 < p.N) v.w = src[3];
-          }
-        }
-        tile[r][c + 0] = v.x; tile[r][c + 1] = v.y; tile[r][c + 2] = v.z; tile[r][c + 3] = v.w;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] = tile[lane][j];
-    };
-    // per-column vector (bias / gamma / beta): same addresses for the whole warp -> broadcast loads
-    auto load_vec = [&](const float* base, int n, float (&t)[32]) {
-      if (vec) {
-        load32(base + n, t);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) t[j] = (n + j < p.N) ? base[n + j] : 0.f;
-      }
-    };
-    auto stage_out = [&](int n, const float (&v)[32]) {
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tile[lane][j] = v[j];
-      __syncwarp();
-      if (p.out_f32) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3), c = (lane & 7) * 4;
-          const int gm = row0 + r;
-          if (gm < p.M) {
-            float* dst = p.out_f32 + (long long)gm * p.ld_out_f32 + n + c;
-            if (vec) {
-              *reinterpret_cast<float4*>(dst) = make_float4(tile[r][c], tile[r][c + 1], tile[r][c + 2], tile[r][c + 3]);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (n + c + k < p.N) dst[k] = tile[r][c + k];
-            }
-          }
-        }
-      }
-      if (p.out_bf16) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 8 + (lane >> 2), c = (lane & 3) * 8;
-          const int gm = row0 + r;
-          if (gm < p.M) {
-            __nv_bfloat16* dst = p.out_bf16 + (long long)gm * p.ld_out_bf16 + n + c;
-            if (vec) {
-              uint4 u;
-              u.x = pack_bf16(tile[r][c + 0], tile[r][c + 1]); u.y = pack_bf16(tile[r][c + 2], tile[r][c + 3]);
-              u.z = pack_bf16(tile[r][c + 4], tile[r][c + 5]); u.w = pack_bf16(tile[r][c + 6], tile[r][c + 7]);
-              *reinterpret_cast<uint4*>(dst) = u;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (n + c + k < p.N) dst[k] = __float2bfloat16_rn(tile[r][c + k]);
-            }
-          }
-        }
-      }
-    };
-
-    const bool gate = (p.row_gate && row_ok) ? (p.row_gate[m] != 0) : true;
-    const bool do_ln = p.ln_gamma != nullptr;
-    float s1 = 0.f, s2 = 0.f;
-
-    // pass 1: accumulator -> pre-activation row value (bias, row bias, gate, residuals)
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    // pre-activation row chunk: accumulator (+ bias when it was not folded in); gated-off rows keep only the residuals
+    auto load_chunk = [&](int c, float (&v)[32]) {
       uint32_t r[32];
       tmem_ld32(trow + c * 32, r);
-      const int n = n0 + c * 32;
-      float v[32], t[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.bias) { load_vec(p.bias, n, t);
+      if (!p.has_init && p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += t[j]; }
-      if (p.row_bias) { stage_in(p.row_bias, p.ld_row_bias, p.row_bias_period, n, t);
+        for (int j = 0; j < 32; ++j) v[j] += s_bias[c * 32 + j];
+      }
+      if (!gate) side_terms(c, false, v);
+    };
+    auto store_chunk = [&](int c, float (&v)[32]) {
+      const int nc = ncols - c * 32;
+      if (!row_ok || nc <= 0) return;
+      const int n = n0 + c * 32;
+      if (p.post_add) add_row32(p.post_add + (long long)m * p.ld_post_add + n, nc, vec, v);
+      if (vec && nc >= 32) {
+        if (p.out_f32) {
+          float* dst = p.out_f32 + (long long)m * p.ld_out_f32 + n;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += t[j]; }
-      if (!gate) {
+          for (int i = 0; i < 4; ++i) st256(dst + 8 * i, v + 8 * i);
+        }
+        if (p.out_bf16) {
+          uint32_t u[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f; }
-      if (p.residual) { stage_in(p.residual, p.ld_residual, 0, n, t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += t[j]; }
-      if (p.residual2) { stage_in(p.residual2, p.ld_residual2, 0, n, t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += t[j]; }
-      if (do_ln) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); r[j] = __float_as_uint(v[j]); }
-        tmem_st32(trow + c * 32, r);          // park the pre-norm row in TMEM for pass 2
+          for (int i = 0; i < 16; ++i) u[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+          __nv_bfloat16* dst = p.out_bf16 + (long long)m * p.ld_out_bf16 + n;
+          st256u(dst, u);
+          st256u(dst + 16, u + 8);
+        }
       } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < nc) {
+            if (p.out_f32) p.out_f32[(long long)m * p.ld_out_f32 + n + j] = v[j];
+            if (p.out_bf16) p.out_bf16[(long long)m * p.ld_out_bf16 + n + j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+    };
+
+    if (!kLN) {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= ncols) break;
+        float v[32];
+        load_chunk(c, v);
         if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f); }
-        if (p.post_add) { stage_in(p.post_add, p.ld_post_add, 0, n, t);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += t[j]; }
-        stage_out(n, v);
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        store_chunk(c, v);
       }
-    }
-    if (do_ln) {
-      // pass 2: normalise (biased variance, like nn.LayerNorm), gain/bias, ReLU, post-add, store
+    } else {
+      // LayerNorm over the full row: this CTA holds 64 of its N columns, the cluster holds all of them
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        load_chunk(c, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+      }
+      s_part[row] = make_float2(s1, s2);
+      cluster_sync_all();                                        // #1: every CTA's partial sums are published
+      const uint32_t me = cluster_ctarank(), nct = cluster_nctarank();
+      const uint32_t part_addr = smem_u32(&s_part[row]);
+      for (uint32_t r = 1; r < nct; ++r) {
+        const float2 o = ld_dsmem_f2(part_addr, (me + r) % nct);
+        s1 += o.x; s2 += o.y;
+      }
       const float inv_n = 1.0f / (float)p.N;
       const float mean = s1 * inv_n;
-      const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
+      const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);    // biased variance, like nn.LayerNorm
       const float rstd = rsqrtf(var + p.ln_eps);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(trow + c * 32, r);
-        const int n = n0 + c * 32;
-        float v[32], g[32], b[32];
-        load_vec(p.ln_gamma, n, g);
-        load_vec(p.ln_beta, n, b);
+        float v[32];
+        load_chunk(c, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] = fmaf((__uint_as_float(r[j]) - mean) * rstd, g[j], b[j]);
+          v[j] = fmaf((v[j] - mean) * rstd, s_gamma[c * 32 + j], s_beta[c * 32 + j]);
           if (p.relu) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.post_add) { stage_in(p.post_add, p.ld_post_add, 0, n, g);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += g[j]; }
-        stage_out(n, v);
+        store_chunk(c, v);
       }
     }
     tc_fence_before();
+  }
+  if (kLN) {
+    if (warp < 2) cluster_sync_all();      // #1 for the producer / MMA warps
+    cluster_sync_all();                    // #2: nobody leaves while a peer may still read its partial sums
   }
   __syncthreads();
   if (warp == 1) {
@@ -344,38 +392,49 @@ bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CU
   return true;
 }
 
-template <int BN, bool kVec>
-int launch_bn(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
+template <bool kLN>
+int launch_tile(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
   CUtensorMap ma, mw;
   if (!get_map(a->A, a->lda, a->M, a->K, BM, &ma)) return TC_ERR_SHAPE;
   if (!get_map(a->W, a->ldw, a->N, a->K, BN, &mw)) return TC_ERR_SHAPE;
-  constexpr size_t smem = (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<BN, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { set_error("tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
-  dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN);
-  linear_tc_kernel<BN, kVec><<<grid, kThreads, smem, s>>>(ma, mw, ep);
+  const unsigned ntiles = (unsigned)((a->N + BN - 1) / BN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ntiles, (unsigned)((a->M + BM - 1) / BM));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;       // LayerNorm: the CTAs of one row block exchange row statistics
+  attr[0].val.clusterDim.x = kLN ? ntiles : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, linear_tc_kernel<kLN>, ma, mw, ep);
+  if (e != cudaSuccess) { set_error("tc_linear(tcgen05): %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   count_launch();
   return check_launch("tc_linear(tcgen05)");
 }
 
+inline bool al32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
 
+// 256-bit row accesses: every row-wise operand 32-byte aligned, pitch a multiple of 32 bytes
 static bool epilogue_vectorizable(const tc_linear_args* a) {
-  if (a->N % 32 != 0) return false;
-  if (a->bias && !al16(a->bias)) return false;
-  if (a->row_bias && (!al16(a->row_bias) || a->ld_row_bias % 4 != 0)) return false;
-  if (a->residual && (!al16(a->residual) || a->ld_residual % 4 != 0)) return false;
-  if (a->residual2 && (!al16(a->residual2) || a->ld_residual2 % 4 != 0)) return false;
-  if (a->post_add && (!al16(a->post_add) || a->ld_post_add % 4 != 0)) return false;
-  if (a->ln_gamma && (!al16(a->ln_gamma) || !al16(a->ln_beta))) return false;
-  if (a->out_f32 && (!al16(a->out_f32) || a->ld_out_f32 % 4 != 0)) return false;
-  if (a->out_bf16 && (!al16(a->out_bf16) || a->ld_out_bf16 % 8 != 0)) return false;
+  if (a->row_bias && (!al32(a->row_bias) || a->ld_row_bias % 8 != 0)) return false;
+  if (a->residual && (!al32(a->residual) || a->ld_residual % 8 != 0)) return false;
+  if (a->residual2 && (!al32(a->residual2) || a->ld_residual2 % 8 != 0)) return false;
+  if (a->post_add && (!al32(a->post_add) || a->ld_post_add % 8 != 0)) return false;
+  if (a->out_f32 && (!al32(a->out_f32) || a->ld_out_f32 % 8 != 0)) return false;
+  if (a->out_bf16 && (!al32(a->out_bf16) || a->ld_out_bf16 % 16 != 0)) return false;
   return true;
 }
 
@@ -384,9 +443,8 @@ bool linear_tc_supported(const tc_linear_args* a) {
   if (disabled) return false;
   if (a->a_dtype != TC_BF16 || a->w_dtype != TC_BF16) return false;
   if (a->K % BK != 0 || a->K < BK) return false;
-  const int N = a->N;
-  if (!(N <= 32 || N == 64 || N == 128 || (N % 256 == 0))) return false;
-  if (a->ln_gamma && N != 256) return false;
+  // fused LayerNorm: the row block's CTAs form one cluster (portable size <= 8) -> N = 64, 128 or 256 here
+  if (a->ln_gamma && !(a->N == 64 || a->N == 128 || a->N == 256)) return false;
   // TMA: 16-byte aligned base and row pitch for both operands
   if (!al16(a->A) || !al16(a->W) || (a->lda * 2) % 16 != 0 || (a->ldw * 2) % 16 != 0) return false;
   return true;
@@ -406,12 +464,9 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   ep.post_add = a->post_add; ep.ld_post_add = a->ld_post_add;
   ep.out_f32 = a->out_f32; ep.ld_out_f32 = a->ld_out_f32;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); ep.ld_out_bf16 = a->ld_out_bf16;
-  const bool vec = epilogue_vectorizable(a);
-  ep.vec = vec ? 1 : 0;
-  if (a->N <= 32) return vec ? launch_bn<32, true>(a, ep, s) : launch_bn<32, false>(a, ep, s);
-  if (a->N == 64) return vec ? launch_bn<64, true>(a, ep, s) : launch_bn<64, false>(a, ep, s);
-  if (a->N == 128) return vec ? launch_bn<128, true>(a, ep, s) : launch_bn<128, false>(a, ep, s);
-  return vec ? launch_bn<256, true>(a, ep, s) : launch_bn<256, false>(a, ep, s);
+  ep.vec = epilogue_vectorizable(a) ? 1 : 0;
+  ep.has_init = (a->row_bias || a->residual || a->residual2) ? 1 : 0;
+  return a->ln_gamma ? launch_tile<true>(a, ep, s) : launch_tile<false>(a, ep, s);
 }
 
 }  // namespace tc

@@ -40,6 +40,7 @@ class FusionDecoderEngine:
         self.device = torch.device(device)
         self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
         self.sample_events = None        # set to a list to collect (start, end) CUDA events per K1 launch
+        self.external_events = False     # True while capturing: events become graph nodes (timing inside a graph)
         self.keep_cam_masks = False      # set True to collect the [B,Q,N] validity mask of every layer
         self.cam_masks = []
         self.use_graph = True            # replay the whole forward as one CUDA graph (static shapes)
@@ -156,7 +157,8 @@ class FusionDecoderEngine:
                            row_bias=self.row_bias_aw[l], row_bias_period=Q)
             ev = self.sample_events
             if ev is not None:          # bench.py: per-launch CUDA-event timing of K1 on the launching stream
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0 = torch.cuda.Event(enable_timing=True, external=self.external_events)
+                e1 = torch.cuda.Event(enable_timing=True, external=self.external_events)
                 e0.record()
             s, cam_mask = ops.sample_fwd(feats, ref.view(B, Q, 3), l2i, aw.view(B, Q, -1), self.pc_range, img_w, img_h,
                                          out_dtype=self.act_dtype, want_mask=self.keep_cam_masks)
@@ -318,6 +320,27 @@ class FusionDecoderEngine:
         graph.replay()
         return dict(all_cls_scores=out["all_cls_scores"].clone(), all_bbox_preds=out["all_bbox_preds"].clone(),
                     enc_cls_scores=None, enc_bbox_preds=None)
+
+    @torch.no_grad()
+    def capture_instrumented(self, prepared):
+        """The whole forward as ONE CUDA graph with a pair of external timing events around every K1 (sampling)
+        launch: per-kernel device times measured in place, without the host launch gaps of eager mode.
+        Returns (graph, [(start, end), ...]); replay, synchronize, then read ``start.elapsed_time(end)``."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._forward_eager(prepared)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        self.sample_events, self.external_events = [], True
+        try:
+            with torch.cuda.graph(graph):
+                out = self._forward_eager(prepared)
+            events = self.sample_events
+        finally:
+            self.sample_events, self.external_events = None, False
+        graph._keepalive = out
+        return graph, events
 
     @torch.no_grad()
     def forward_prepared(self, prepared, return_aux=False):
