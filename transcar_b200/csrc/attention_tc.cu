@@ -28,6 +28,12 @@ constexpr uint32_t kTileBytes = kBKV * kD * 2;          // 8 KB: one Q / K / V t
 constexpr uint32_t kPHalfBytes = kBQ * 64 * 2;          // 16 KB: P for 64 keys
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnTcParams {
   int B, Lq, Lk, heads;
   float scale_log2;                 // scale * log2(e)
@@ -119,11 +125,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const int s = j & 1;
         mbar_wait(p_full, j & 1);                 // P(j) in smem, O rescaled, S(j) consumed
         tc_fence_after();
+        // the tail tile multiplies only the 16-key groups that hold real keys (P is not written beyond them)
+        const int ksteps = (min(kBKV, p.Lk - j * kBKV) + 15) >> 4;
 #pragma unroll
         for (int k16 = 0; k16 < kBKV / 16; ++k16) {
-          const uint64_t dp = make_desc_sw128(sbase + kOffP + (k16 >> 2) * kPHalfBytes) + 2 * (k16 & 3);
-          const uint64_t dv = make_desc_sw64_mnmajor(sbase + kOffV + s * kTileBytes + k16 * 1024, 8192);
-          umma_bf16(tmem_O, dp, dv, idesc_o, (j | k16) ? 1u : 0u);
+          if (k16 < ksteps) {
+            const uint64_t dp = make_desc_sw128(sbase + kOffP + (k16 >> 2) * kPHalfBytes) + 2 * (k16 & 3);
+            const uint64_t dv = make_desc_sw64_mnmajor(sbase + kOffV + s * kTileBytes + k16 * 1024, 8192);
+            umma_bf16(tmem_O, dp, dv, idesc_o, (j | k16) ? 1u : 0u);
+          }
         }
         umma_commit(kv_empty + 8 * s);            // K/V stage s may be refilled
         umma_commit(o_done);                      // O(j) accumulated, P buffer free
@@ -161,6 +171,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
     for (int j = 0; j < T; ++j) {
       const int k0 = j * kBKV;
+      const int nvalid = min(kBKV, p.Lk - k0);          // real keys in this tile
+      const int nchunks = (nvalid + 31) >> 5;           // 32-key chunks that hold at least one real key
       float* kx = key_geo + (j & 1) * 3 * kBKV;
       float* ky = kx + kBKV;
       float* kn = ky + kBKV;
@@ -176,75 +188,136 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-
-      // ---- pass A: scaled, masked row maximum; remember which keys are allowed -------------------------
-      uint32_t allow[4];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, r);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kk = c * 32 + i;
-          bool ok = (k0 + kk) < p.Lk;
-          if (kMask) {
-            // cdist(mm route) < radius, evaluated on squared distances: acc < thr  (thr: smallest float whose sqrt >= r)
-            const float x = kx[kk], y = ky[kk], n = kn[kk];
-            const float dc = __fmaf_rn(1.0f, n, __fmaf_rn(cc.nrm, 1.0f, __fmaf_rn(cc.m2y, y, __fmul_rn(cc.m2x, x))));
-            const float df = __fmaf_rn(1.0f, n, __fmaf_rn(cf.nrm, 1.0f, __fmaf_rn(cf.m2y, y, __fmul_rn(cf.m2x, x))));
-            const float dr = __fmaf_rn(1.0f, n, __fmaf_rn(cr.nrm, 1.0f, __fmaf_rn(cr.m2y, y, __fmul_rn(cr.m2x, x))));
-            ok = ok && ((dc < thr) | (df < thr) | (dr < thr));
-          }
-          if (ok) {
-            bits |= 1u << i;
-            mx = fmaxf(mx, __uint_as_float(r[i]) * p.scale_log2);
-          }
-        }
-        allow[c] = bits;
+      if (q0 + quad * 32 >= p.Lq) {                     // whole warp past Lq (warp-uniform: tcgen05.ld/st are warp-collective):
+                                                        // keep the barrier protocol, skip the math
+        tc_fence_before();
+        mbar_arrive(p_full);
+        continue;
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = (m_new == -INFINITY) ? 1.0f : exp2f(m_run - m_new);      // m_run = -inf -> 0
-      l_run *= corr;
-
-      // ---- O rescale (needs PV(j-1) retired; also frees the P buffer) ------------------------------------
-      if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, corr != 1.0f)) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_off, o);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-          tmem_st32(tmem_O + lane_off, o);
-        }
-      }
-
-      // ---- pass B: probabilities -> bf16 P in shared memory (K-major, 128B swizzle) ----------------------
       uint8_t* prow = smem + kOffP + row * 128;
+
+      if (!kMask && nvalid == kBKV) {
+        // ======== fast path: full, mask-free tile (decoder self-attention): ~4.5 instructions per (query, key) ========
+        float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, r);
-        float pv[32];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, r);
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
-          pv[i] = ((allow[c] >> i) & 1u) ? e : 0.f;
-          l_run += pv[i];
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
         }
-        uint8_t* half = prow + (c >> 1) * kPHalfBytes;
+        const float m_new = fmaxf(m_run, mx * p.scale_log2);       // scale > 0 (checked on the host)
+        const float corr = ex2_approx(m_run - m_new);               // m_run = -inf -> 0
+        if (j > 0) {
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, corr != 1.0f)) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off, o);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {          // 4 x 16-byte chunks = 32 keys
-          uint4 u;
-          u.x = pack_bf16(pv[8 * g + 0], pv[8 * g + 1]); u.y = pack_bf16(pv[8 * g + 2], pv[8 * g + 3]);
-          u.z = pack_bf16(pv[8 * g + 4], pv[8 * g + 5]); u.w = pack_bf16(pv[8 * g + 6], pv[8 * g + 7]);
-          const int chunk = (c & 1) * 4 + g;
-          *reinterpret_cast<uint4*>(half + ((chunk ^ (row & 7)) << 4)) = u;
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tmem_st32(tmem_O + lane_off, o);
+          }
         }
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, r);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_new));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_new));
+            l4[i & 3] += e0 + e1;
+            pk[i] = pack_bf16(e0, e1);
+          }
+          uint8_t* half = prow + (c >> 1) * kPHalfBytes;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {          // 4 x 16-byte chunks = 32 keys
+            const int chunk = (c & 1) * 4 + g;
+            *reinterpret_cast<uint4*>(half + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
+        }
+        l_run = fmaf(l_run, corr, (l4[0] + l4[1]) + (l4[2] + l4[3]));
+        m_run = m_new;
+      } else {
+        // ======== general path: radar mask and / or a partial last tile ========
+        // ---- pass A: scaled, masked row maximum; remember which keys are allowed -------------------------
+        uint32_t allow[4] = {0u, 0u, 0u, 0u};
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunks) {
+            uint32_t r[32];
+            tmem_ld32(tmem_S + lane_off + c * 32, r);
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int kk = c * 32 + i;
+              bool ok = kk < nvalid;
+              if (kMask) {
+                // cdist(mm route) < radius, evaluated on squared distances: acc < thr  (thr: smallest float whose sqrt >= r)
+                const float x = kx[kk], y = ky[kk], n = kn[kk];
+                const float dc = __fmaf_rn(1.0f, n, __fmaf_rn(cc.nrm, 1.0f, __fmaf_rn(cc.m2y, y, __fmul_rn(cc.m2x, x))));
+                const float df = __fmaf_rn(1.0f, n, __fmaf_rn(cf.nrm, 1.0f, __fmaf_rn(cf.m2y, y, __fmul_rn(cf.m2x, x))));
+                const float dr = __fmaf_rn(1.0f, n, __fmaf_rn(cr.nrm, 1.0f, __fmaf_rn(cr.m2y, y, __fmul_rn(cr.m2x, x))));
+                ok = ok && ((dc < thr) | (df < thr) | (dr < thr));
+              }
+              if (ok) {
+                bits |= 1u << i;
+                mx = fmaxf(mx, __uint_as_float(r[i]) * p.scale_log2);
+              }
+            }
+            allow[c] = bits;
+          }
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float corr = (m_new == -INFINITY) ? 1.0f : exp2f(m_run - m_new);      // m_run = -inf -> 0
+        l_run *= corr;
+
+        // ---- O rescale (needs PV(j-1) retired; also frees the P buffer) ------------------------------------
+        if (j > 0) {
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, corr != 1.0f)) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off, o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tmem_st32(tmem_O + lane_off, o);
+          }
+        }
+
+        // ---- pass B: probabilities -> bf16 P in shared memory (K-major, 128B swizzle) ----------------------
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunks) {
+            uint32_t r[32];
+            tmem_ld32(tmem_S + lane_off + c * 32, r);
+            float pv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
+              pv[i] = ((allow[c] >> i) & 1u) ? e : 0.f;
+              l_run += pv[i];
+            }
+            uint8_t* half = prow + (c >> 1) * kPHalfBytes;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {          // 4 x 16-byte chunks = 32 keys
+              uint4 u;
+              u.x = pack_bf16(pv[8 * g + 0], pv[8 * g + 1]); u.y = pack_bf16(pv[8 * g + 2], pv[8 * g + 3]);
+              u.z = pack_bf16(pv[8 * g + 4], pv[8 * g + 5]); u.w = pack_bf16(pv[8 * g + 6], pv[8 * g + 7]);
+              const int chunk = (c & 1) * 4 + g;
+              *reinterpret_cast<uint4*>(half + ((chunk ^ (row & 7)) << 4)) = u;
+            }
+          }
+        }
+        m_run = m_new;
       }
-      m_run = m_new;
       fence_proxy_async_smem();                // generic-proxy smem writes -> visible to the MMA (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
@@ -344,7 +417,7 @@ bool attention_tc_supported(const tc_attention_args* a) {
   static const bool disabled = getenv("TC_DISABLE_TC_ATTENTION") != nullptr;     // debugging / A-B measurements
   if (disabled) return false;
   if (a->qkv_dtype != TC_BF16 || a->out_dtype != TC_BF16) return false;
-  if (a->D != kD || a->Lk <= 0) return false;
+  if (a->D != kD || a->Lk <= 0 || !(a->scale > 0.f)) return false;
   const int E = a->heads * a->D;
   (void)E;
   // TMA: 16-byte aligned bases / pitches (checked by the caller), batch stride a multiple of 16 bytes

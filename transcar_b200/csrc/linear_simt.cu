@@ -203,6 +203,64 @@ __global__ void __launch_bounds__(128) point_embed_kernel(const PointEmbedParams
   }
 }
 
+// C == 256 specialisation: persistent warps, lane owns channels [8*lane, 8*lane+8) and keeps their 24 weights,
+// bias, gain and shift in registers across rows.  The parameters reach the registers through one coalesced,
+// transposed shared-memory copy per CTA (a direct per-lane read of weight[c][k] costs 24 L1 wavefronts per load).
+__global__ void __launch_bounds__(256) point_embed256_kernel(const PointEmbedParams p) {
+  __shared__ __align__(16) float s_par[6 * 256];          // w[k=0..2][c], bias[c], gamma[c], beta[c]
+  for (int f = threadIdx.x; f < 768; f += 256) s_par[(f % 3) * 256 + f / 3] = __ldg(p.weight + f);
+  s_par[768 + threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  s_par[1024 + threadIdx.x] = __ldg(p.gamma + threadIdx.x);
+  s_par[1280 + threadIdx.x] = __ldg(p.beta + threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 8;
+  float w[8][3], bias[8], gamma[8], beta[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 t = *reinterpret_cast<const float4*>(s_par + k * 256 + c0 + 4 * h);
+      w[4 * h + 0][k] = t.x; w[4 * h + 1][k] = t.y; w[4 * h + 2][k] = t.z; w[4 * h + 3][k] = t.w;
+    }
+    const float4 tb = *reinterpret_cast<const float4*>(s_par + 768 + c0 + 4 * h);
+    const float4 tg = *reinterpret_cast<const float4*>(s_par + 1024 + c0 + 4 * h);
+    const float4 te = *reinterpret_cast<const float4*>(s_par + 1280 + c0 + 4 * h);
+    bias[4 * h + 0] = tb.x; bias[4 * h + 1] = tb.y; bias[4 * h + 2] = tb.z; bias[4 * h + 3] = tb.w;
+    gamma[4 * h + 0] = tg.x; gamma[4 * h + 1] = tg.y; gamma[4 * h + 2] = tg.z; gamma[4 * h + 3] = tg.w;
+    beta[4 * h + 0] = te.x; beta[4 * h + 1] = te.y; beta[4 * h + 2] = te.z; beta[4 * h + 3] = te.w;
+  }
+  const int stride = gridDim.x * 8;
+  for (int m = blockIdx.x * 8 + (threadIdx.x >> 5); m < p.M; m += stride) {
+    const float* xr = p.x + (long long)m * p.ldx;
+    float x0 = __ldg(xr), x1 = __ldg(xr + 1), x2 = __ldg(xr + 2);
+    if (p.logit) { x0 = logit_f32(x0); x1 = logit_f32(x1); x2 = logit_f32(x2); }
+    float y[8], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      y[i] = fmaf(x2, w[i][2], fmaf(x1, w[i][1], x0 * w[i][0])) + bias[i];     // k order, then + bias (addmm)
+      s += y[i];
+    }
+    const float mean = warp_sum(s) * (1.0f / 256.0f);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = y[i] - mean; sq = fmaf(d, d, sq); }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / 256.0f) + p.eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = fmaxf((y[i] - mean) * rstd * gamma[i] + beta[i], 0.f);
+    if (p.out_f32) {
+      float4* o = reinterpret_cast<float4*>(p.out_f32 + (long long)m * 256 + c0);
+      o[0] = make_float4(y[0], y[1], y[2], y[3]);
+      o[1] = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    if (p.out_bf16) {
+      uint4 u;
+      u.x = pack_bf16(y[0], y[1]); u.y = pack_bf16(y[2], y[3]); u.z = pack_bf16(y[4], y[5]); u.w = pack_bf16(y[6], y[7]);
+      *reinterpret_cast<uint4*>(p.out_bf16 + (long long)m * 256 + c0) = u;
+    }
+  }
+}
+
 }  // namespace
 
 int linear_simt_launch(const tc_linear_args* a, cudaStream_t s) {
@@ -244,7 +302,13 @@ extern "C" int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream) 
   if (a->M == 0) return TC_OK;
   PointEmbedParams p{a->x, a->ldx, a->M, a->C, a->logit_input, a->weight, a->bias, a->ln_gamma, a->ln_beta,
                      a->ln_eps, a->out_f32, static_cast<__nv_bfloat16*>(a->out_bf16)};
-  point_embed_kernel<<<(a->M + 3) / 4, 128, 0, as_stream(stream)>>>(p);
+  const bool al = (!a->out_f32 || aligned16(a->out_f32)) && (!a->out_bf16 || aligned16(a->out_bf16));
+  if (a->C == 256 && al) {
+    const int ctas = (a->M + 7) / 8;
+    point_embed256_kernel<<<ctas < 296 ? ctas : 296, 256, 0, as_stream(stream)>>>(p);      // 2 CTAs per SM x 148
+  } else {
+    point_embed_kernel<<<(a->M + 3) / 4, 128, 0, as_stream(stream)>>>(p);
+  }
   count_launch();
   return check_launch("tc_point_embed");
 }

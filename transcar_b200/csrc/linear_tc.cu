@@ -217,14 +217,46 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     };
 
     if (p.has_init) {
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        uint32_t r[32];
-        side_terms(c, gate, v);
+      if (vec && ncols == BN) {
+        // all 64 columns of a tensor are requested before the first one is consumed (8 x 256-bit loads in flight)
+        float v[BN];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-        tmem_st32(trow + c * 32, r);
+        for (int j = 0; j < BN; ++j) v[j] = 0.f;
+        if (row_ok) {
+          auto add64 = [&](const float* src) {
+            float t[BN];
+#pragma unroll
+            for (int i = 0; i < BN / 8; ++i) ld256(src + 8 * i, t + 8 * i);
+#pragma unroll
+            for (int j = 0; j < BN; ++j) v[j] += t[j];
+          };
+          if (gate) {
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < BN; ++j) v[j] = s_bias[j];
+            }
+            if (p.row_bias) add64(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n0);
+          }
+          if (p.residual) add64(p.residual + (long long)m * p.ld_residual + n0);
+          if (p.residual2) add64(p.residual2 + (long long)m * p.ld_residual2 + n0);
+        }
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[c * 32 + j]);
+          tmem_st32(trow + c * 32, r);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          uint32_t r[32];
+          side_terms(c, gate, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+          tmem_st32(trow + c * 32, r);
+        }
       }
       tc_fence_before();
       mbar_arrive(initbar);

@@ -15,6 +15,23 @@ from ._lib import TC_BF16, TC_F32
 
 _DT = {torch.float32: TC_F32, torch.bfloat16: TC_BF16}
 
+# Profiling hook (tools/step_timeline.py): when set to a list, every library call is bracketed by a pair of CUDA
+# events (external=True, so the pair becomes two nodes of a captured CUDA graph) and (label, start, end) is appended.
+TIMELINE = None
+TIMELINE_EXTERNAL = True
+
+
+def _call(label, fn, *args):
+    if TIMELINE is None:
+        return fn(*args)
+    e0 = torch.cuda.Event(enable_timing=True, external=TIMELINE_EXTERNAL)
+    e1 = torch.cuda.Event(enable_timing=True, external=TIMELINE_EXTERNAL)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    TIMELINE.append((label, e0, e1))
+    return rc
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -61,7 +78,7 @@ def to_channels_last(f, dtype=None):
     _need(f, "feat")
     out = torch.empty((B, N, H, W, Cc), device=f.device, dtype=dtype)
     lib = _lib.load()
-    _lib.check(lib.tc_nchw_to_nhwc(_ptr(f), _ptr(out), _DT[dtype], B * N, Cc, H * W, _stream()), "nchw_to_nhwc")
+    _lib.check(_call("nchw_to_nhwc", lib.tc_nchw_to_nhwc, _ptr(f), _ptr(out), _DT[dtype], B * N, Cc, H * W, _stream()), "nchw_to_nhwc")
     return out.permute(0, 1, 4, 2, 3)
 
 
@@ -98,7 +115,7 @@ def sample_fwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, out_d
     a.img_w, a.img_h = float(img_w), float(img_h)
     a.out = out.data_ptr()
     a.mask = mask.data_ptr() if mask is not None else None
-    _lib.check(lib.tc_sample_fwd(C.byref(a), _stream()), "sample_fwd")
+    _lib.check(_call("sample", lib.tc_sample_fwd, C.byref(a), _stream()), "sample_fwd")
     return out, mask
 
 
@@ -155,7 +172,12 @@ def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, 
     if out_bf16 is not None:
         o, ldo = _rows(_need(out_bf16, "out_bf16", torch.bfloat16), "out_bf16")
         a.out_bf16, a.ld_out_bf16 = o.data_ptr(), ldo
-    _lib.check(lib.tc_linear(C.byref(a), _stream()), "linear")
+    label = "linear" if TIMELINE is None else (
+        f"linear M{M} N{N} K{K} {'bf16' if A.dtype == torch.bfloat16 else 'f32'}" + ("+rb" if row_bias is not None else "") +
+        ("+gate" if row_gate is not None else "") + ("+res" if residual is not None else "") +
+        ("+res2" if residual2 is not None else "") + ("+ln" if ln is not None else "") + ("+relu" if relu else "") +
+        ("+post" if post_add is not None else ""))
+    _lib.check(_call(label, lib.tc_linear, C.byref(a), _stream()), "linear")
     return out_f32, out_bf16
 
 
@@ -174,7 +196,7 @@ def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, wa
     o32 = torch.empty((M, Cc), device=x.device, dtype=torch.float32) if want_f32 else None
     o16 = torch.empty((M, Cc), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     a.out_f32, a.out_bf16 = _ptr(o32), _ptr(o16)
-    _lib.check(lib.tc_point_embed(C.byref(a), _stream()), "point_embed")
+    _lib.check(_call(f"point_embed M{M}", lib.tc_point_embed, C.byref(a), _stream()), "point_embed")
     return o32, o16
 
 
@@ -212,7 +234,7 @@ def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_ro
     a.out, a.ldo, a.out_dtype = out.data_ptr(), out.stride(1), _DT[out.dtype]
     a.row_any = _ptr(row_any)
     a.algo = ATTN_ALGOS[algo]
-    _lib.check(lib.tc_attention_fwd(C.byref(a), _stream()), "attention")
+    _lib.check(_call(f"attention Lq{Lq} Lk{Lk} {algo}{' masked' if geom is not None else ''}", lib.tc_attention_fwd, C.byref(a), _stream()), "attention")
     return out, row_any
 
 
@@ -230,7 +252,7 @@ def radar_geometry(centre, code, pc_range, r_lo, r_hi, centre_is_normalised):
         a.pc_range[i] = float(pc_range[i])
     a.r_lo, a.r_hi = float(r_lo), float(r_hi)
     a.geom = geom.data_ptr()
-    _lib.check(lib.tc_radar_geometry(C.byref(a), _stream()), "radar_geometry")
+    _lib.check(_call("radar_geometry", lib.tc_radar_geometry, C.byref(a), _stream()), "radar_geometry")
     return geom
 
 
@@ -255,7 +277,7 @@ def ref_update(code, ref, out=None):
     M = code.shape[0]
     if out is None:
         out = torch.empty((M, 3), device=code.device, dtype=torch.float32)
-    _lib.check(lib.tc_ref_update(_ptr(code), ldc, _ptr(ref), _ptr(out), M, _stream()), "ref_update")
+    _lib.check(_call("ref_update", lib.tc_ref_update, _ptr(code), ldc, _ptr(ref), _ptr(out), M, _stream()), "ref_update")
     return out
 
 
@@ -265,8 +287,8 @@ def box_anchor_add(code, anchor, xy_col, z_col, xy_from_normalised, pc_range):
     code, ldc = _rows(_need(code, "code", torch.float32), "code")
     anchor, lda = _rows(_need(anchor, "anchor", torch.float32), "anchor")
     pc = (C.c_float * 6)(*[float(x) for x in pc_range])
-    _lib.check(lib.tc_box_anchor_add(_ptr(code), ldc, _ptr(anchor), lda, xy_col, z_col,
-                                     1 if xy_from_normalised else 0, C.byref(pc), code.shape[0], _stream()),
+    _lib.check(_call("box_anchor_add", lib.tc_box_anchor_add, _ptr(code), ldc, _ptr(anchor), lda, xy_col, z_col,
+                     1 if xy_from_normalised else 0, C.byref(pc), code.shape[0], _stream()),
                "box_anchor_add")
     return code
 
