@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(kRows) attention_simt_kernel(const AttnParams 
 
 // ---- radar geometry + materialised mask -------------------------------------------------------------
 __global__ void radar_geometry_kernel(const tc_radar_geometry_args a) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= a.M) return;
   float cx = a.centre[(long long)m * a.ld_centre + 0], cy = a.centre[(long long)m * a.ld_centre + 1];
@@ -261,7 +263,7 @@ extern "C" int tc_radar_geometry(const tc_radar_geometry_args* a, tc_stream_t st
   TC_REQUIRE(a->centre && a->code && a->geom, TC_ERR_NULL, "tc_radar_geometry: NULL pointer");
   TC_REQUIRE(a->M >= 0 && a->ld_centre >= 2 && a->ld_code >= 8, TC_ERR_SHAPE, "tc_radar_geometry: bad shape");
   if (a->M == 0) return TC_OK;
-  radar_geometry_kernel<<<(a->M + 127) / 128, 128, 0, as_stream(stream)>>>(*a);
+  launch(radar_geometry_kernel, dim3((a->M + 127) / 128), dim3(128), 0, as_stream(stream), 1u, *a);
   count_launch();
   return check_launch("tc_radar_geometry");
 }

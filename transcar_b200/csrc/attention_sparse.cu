@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(kWarps * 32) attention_sparse_kernel(const Spa
   const int b = blockIdx.y;
   const bool active = q < p.Lq;
   const long long row = (long long)b * p.Lq + (active ? q : 0);
+  pdl_trigger();
+  pdl_wait();
 
   const float* g = p.geom + row * 8;
   const float cx = __ldg(g + 0), cy = __ldg(g + 1), fx = __ldg(g + 2), fy = __ldg(g + 3);
@@ -153,10 +155,10 @@ int attention_sparse_launch(const tc_attention_args* a, cudaStream_t s) {
   p.out = a->out; p.ldo = a->ldo; p.row_any = a->row_any;
   dim3 grid((a->Lq + kWarps - 1) / kWarps, a->B);
   const bool bi = a->qkv_dtype == TC_BF16, bo = a->out_dtype == TC_BF16;
-  if (bi && bo) attention_sparse_kernel<true, true><<<grid, kWarps * 32, 0, s>>>(p);
-  else if (bi) attention_sparse_kernel<true, false><<<grid, kWarps * 32, 0, s>>>(p);
-  else if (bo) attention_sparse_kernel<false, true><<<grid, kWarps * 32, 0, s>>>(p);
-  else attention_sparse_kernel<false, false><<<grid, kWarps * 32, 0, s>>>(p);
+  if (bi && bo) launch(attention_sparse_kernel<true, true>, grid, dim3(kWarps * 32), 0, s, 1u, p);
+  else if (bi) launch(attention_sparse_kernel<true, false>, grid, dim3(kWarps * 32), 0, s, 1u, p);
+  else if (bo) launch(attention_sparse_kernel<false, true>, grid, dim3(kWarps * 32), 0, s, 1u, p);
+  else launch(attention_sparse_kernel<false, false>, grid, dim3(kWarps * 32), 0, s, 1u, p);
   count_launch();
   return check_launch("tc_attention_fwd(sparse)");
 }

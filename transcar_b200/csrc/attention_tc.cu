@@ -71,6 +71,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
   const int T = (p.Lk + kBKV - 1) / kBKV;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -90,6 +91,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  pdl_wait();            // q / k / v / geometry come from the previous kernels
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -448,8 +450,9 @@ int attention_tc_launch(const tc_attention_args* a, cudaStream_t s) {
   }
   static_assert(kSmemUsed + 1024 <= kSmemBytes, "shared-memory carve-up exceeds the request");
   dim3 grid((a->Lq + kBQ - 1) / kBQ, a->heads, a->B);
-  if (a->geom) attention_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mq, mk, mv, p);
-  else attention_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(mq, mk, mv, p);
+  cudaError_t le = a->geom ? launch(attention_tc_kernel<true>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p)
+                           : launch(attention_tc_kernel<false>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p);
+  if (le != cudaSuccess) { set_error("tc_attention_fwd(tcgen05): %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return (int)le; }
   count_launch();
   return check_launch("tc_attention_fwd(tcgen05)");
 }

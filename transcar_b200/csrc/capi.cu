@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -25,6 +26,11 @@ int check_launch(const char* what) {
     return (int)e;
   }
   return TC_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("TC_DISABLE_PDL") == nullptr;
+  return on;
 }
 
 int linear_simt_launch(const tc_linear_args* a, cudaStream_t s);

@@ -66,6 +66,8 @@ template <typename TA, typename TW>
 __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) {
   __shared__ __align__(16) float As[BK][BM];
   __shared__ __align__(16) float Ws[BK][BN];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const TA* A = static_cast<const TA*>(p.A);
@@ -213,6 +215,8 @@ __global__ void __launch_bounds__(256) point_embed256_kernel(const PointEmbedPar
   s_par[1024 + threadIdx.x] = __ldg(p.gamma + threadIdx.x);
   s_par[1280 + threadIdx.x] = __ldg(p.beta + threadIdx.x);
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();            // parameters above are constants; x comes from the previous kernel
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 8;
   float w[8][3], bias[8], gamma[8], beta[8];
@@ -282,10 +286,10 @@ int linear_simt_launch(const tc_linear_args* a, cudaStream_t s) {
   p.vec_a = (a->K % 4 == 0) && ((a->lda * ea) % (4 * ea) == 0) && ((reinterpret_cast<uintptr_t>(a->A) % (4 * ea)) == 0);
   p.vec_w = (a->K % 4 == 0) && ((a->ldw * ew) % (4 * ew) == 0) && ((reinterpret_cast<uintptr_t>(a->W) % (4 * ew)) == 0);
   dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN);
-  if (a->a_dtype == TC_F32 && a->w_dtype == TC_F32) linear_simt_kernel<float, float><<<grid, 256, 0, s>>>(p);
-  else if (a->a_dtype == TC_BF16 && a->w_dtype == TC_BF16) linear_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(p);
-  else if (a->a_dtype == TC_F32 && a->w_dtype == TC_BF16) linear_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>(p);
-  else linear_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>(p);
+  if (a->a_dtype == TC_F32 && a->w_dtype == TC_F32) launch(linear_simt_kernel<float, float>, grid, dim3(256), 0, s, 1u, p);
+  else if (a->a_dtype == TC_BF16 && a->w_dtype == TC_BF16) launch(linear_simt_kernel<__nv_bfloat16, __nv_bfloat16>, grid, dim3(256), 0, s, 1u, p);
+  else if (a->a_dtype == TC_F32 && a->w_dtype == TC_BF16) launch(linear_simt_kernel<float, __nv_bfloat16>, grid, dim3(256), 0, s, 1u, p);
+  else launch(linear_simt_kernel<__nv_bfloat16, float>, grid, dim3(256), 0, s, 1u, p);
   count_launch();
   return check_launch("tc_linear(simt)");
 }
@@ -305,7 +309,7 @@ extern "C" int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream) 
   const bool al = (!a->out_f32 || aligned16(a->out_f32)) && (!a->out_bf16 || aligned16(a->out_bf16));
   if (a->C == 256 && al) {
     const int ctas = (a->M + 7) / 8;
-    point_embed256_kernel<<<ctas < 296 ? ctas : 296, 256, 0, as_stream(stream)>>>(p);      // 2 CTAs per SM x 148
+    launch(point_embed256_kernel, dim3(ctas < 296 ? ctas : 296), dim3(256), 0, as_stream(stream), 1u, p);      // 2 CTAs per SM x 148
   } else {
     point_embed_kernel<<<(a->M + 3) / 4, 128, 0, as_stream(stream)>>>(p);
   }

@@ -128,6 +128,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int num_kb = p.K / BK;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -138,16 +139,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {          // column vectors of this tile (zero beyond N)
-    const int j = threadIdx.x - 64, n = n0 + j;
-    s_bias[j] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
-    s_gamma[j] = (kLN && n < p.N) ? p.ln_gamma[n] : 0.f;
-    s_beta[j] = (kLN && n < p.N) ? p.ln_beta[n] : 0.f;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();            // everything above touched parameters only; activations are read from here on
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -198,6 +194,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool vec = p.vec != 0;
     const int ncols = min(BN, p.N - n0);
     const bool gate = (p.row_gate && row_ok) ? (p.row_gate[m] != 0) : true;
+    {                                                          // column vectors of this tile (zero beyond N)
+      const int j = threadIdx.x - 64;
+      if (j < BN) {
+        const int n = n0 + j;
+        s_bias[j] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+        s_gamma[j] = (kLN && n < p.N) ? p.ln_gamma[n] : 0.f;
+        s_beta[j] = (kLN && n < p.N) ? p.ln_beta[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+    }
 
     // input-side terms of columns [c*32, c*32+32): (gate ? bias + row_bias : 0) + residual + residual2
     auto side_terms = [&](int c, bool with_gated, float (&v)[32]) {
@@ -436,19 +442,9 @@ int launch_tile(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
     configured = true;
   }
   const unsigned ntiles = (unsigned)((a->N + BN - 1) / BN);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ntiles, (unsigned)((a->M + BM - 1) / BM));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;       // LayerNorm: the CTAs of one row block exchange row statistics
-  attr[0].val.clusterDim.x = kLN ? ntiles : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, linear_tc_kernel<kLN>, ma, mw, ep);
+  // LayerNorm: the CTAs of one row block form a cluster and exchange row statistics
+  cudaError_t e = launch(linear_tc_kernel<kLN>, dim3(ntiles, (unsigned)((a->M + BM - 1) / BM)), dim3(kThreads), kSmemBytes, s,
+                         kLN ? ntiles : 1u, ma, mw, ep);
   if (e != cudaSuccess) { set_error("tc_linear(tcgen05): %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   count_launch();
   return check_launch("tc_linear(tcgen05)");

@@ -7,6 +7,8 @@ namespace {
 // T:195-203: new_ref = sigmoid(code[{0,1,4}] + inverse_sigmoid(ref))
 __global__ void ref_update_kernel(const float* __restrict__ code, long long ld_code, const float* __restrict__ ref,
                                   float* __restrict__ out, int M) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * 3) return;
   const int m = i / 3, a = i % 3;
@@ -19,6 +21,8 @@ struct AnchorParams {
   int xy_col, z_col, from_norm, M; float pc[6];
 };
 __global__ void box_anchor_add_kernel(const AnchorParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= p.M) return;
   const float* an = p.anchor + (long long)m * p.ld_anchor;
@@ -113,7 +117,7 @@ extern "C" int tc_ref_update(const float* code, int64_t ld_code, const float* re
   TC_REQUIRE(code && ref && new_ref, TC_ERR_NULL, "tc_ref_update: NULL pointer");
   TC_REQUIRE(M >= 0 && ld_code >= 5, TC_ERR_SHAPE, "tc_ref_update: bad shape");
   if (M == 0) return TC_OK;
-  ref_update_kernel<<<(M * 3 + 255) / 256, 256, 0, as_stream(stream)>>>(code, ld_code, ref, new_ref, M);
+  launch(ref_update_kernel, dim3((M * 3 + 255) / 256), dim3(256), 0, as_stream(stream), 1u, code, ld_code, ref, new_ref, M);
   count_launch();
   return check_launch("tc_ref_update");
 }
@@ -128,7 +132,7 @@ extern "C" int tc_box_anchor_add(float* code, int64_t ld_code, const float* anch
   if (M == 0) return TC_OK;
   AnchorParams p{code, ld_code, anchor, ld_anchor, xy_col, z_col, xy_from_normalised, M, {}};
   for (int i = 0; i < 6; ++i) p.pc[i] = pc_range6[i];
-  box_anchor_add_kernel<<<(M + 127) / 128, 128, 0, as_stream(stream)>>>(p);
+  launch(box_anchor_add_kernel, dim3((M + 127) / 128), dim3(128), 0, as_stream(stream), 1u, p);
   count_launch();
   return check_launch("tc_box_anchor_add");
 }

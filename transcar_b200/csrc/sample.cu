@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SamplePara
 
   int task = blockIdx.x * kWarps + warp;
   QueryIn cur, nxt;
+  pdl_trigger();
+  pdl_wait();            // reference points and logits come from the previous kernels
   if (task < total) fetch_query(p, task, lane, cur);
   nxt = cur;
 
@@ -351,10 +353,10 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   dim3 block(kWarps * 32);
   cudaStream_t s = as_stream(stream);
   const bool bi = a->feat_dtype == TC_BF16, bo = a->out_dtype == TC_BF16;
-  if (bi && bo) sample_kernel<true, true><<<grid, block, kSampleSmem, s>>>(p);
-  else if (bi) sample_kernel<true, false><<<grid, block, kSampleSmem, s>>>(p);
-  else if (bo) sample_kernel<false, true><<<grid, block, kSampleSmem, s>>>(p);
-  else sample_kernel<false, false><<<grid, block, kSampleSmem, s>>>(p);
+  if (bi && bo) launch(sample_kernel<true, true>, grid, block, kSampleSmem, s, 1u, p);
+  else if (bi) launch(sample_kernel<true, false>, grid, block, kSampleSmem, s, 1u, p);
+  else if (bo) launch(sample_kernel<false, true>, grid, block, kSampleSmem, s, 1u, p);
+  else launch(sample_kernel<false, false>, grid, block, kSampleSmem, s, 1u, p);
   count_launch();
   return check_launch("tc_sample_fwd");
 }
