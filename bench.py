@@ -277,8 +277,17 @@ def run_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic, traffic_src = None, None
+    import glob
+    for tp in sorted(glob.glob(os.path.join(ROOT, "profiles", "*k1_traffic.json"))):      # latest ncu --set full capture
+        try:
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], os.path.relpath(tp, ROOT)
+        except Exception:
+            pass
     roofline = {"kernel": "sample_kernel (K1 fused camera sampling)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": avg_bytes, "avg_launch_ms": avg_ms,
                 "per_layer_ms": per_layer_ms, "valid_pairs_per_layer": valid_pairs,
                 "first_layer_gbs": per_layer_bytes[0] / (per_layer_ms[0] * 1e-3) / 1e9,
