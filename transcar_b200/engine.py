@@ -44,6 +44,9 @@ class FusionDecoderEngine:
         self.keep_cam_masks = False      # set True to collect the [B,Q,N] validity mask of every layer
         self.cam_masks = []
         self.use_graph = True            # replay the whole forward as one CUDA graph (static shapes)
+        self.use_branches = True         # run independent sub-chains on side streams (parallel graph branches)
+        self._side = None
+        self._keep = []                  # tensors that cross streams stay referenced until the forward ends
         self._graphs = {}
         self._init_cache = {}
         self._prepare(state_dict)
@@ -89,6 +92,42 @@ class FusionDecoderEngine:
                           else f32[n + ".in_proj_weight"][:C].contiguous()) for n in names]
         self.radar_bq = [f32[n + ".in_proj_bias"][:C].contiguous() for n in names]
         torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------ parallel branches
+    # Several sub-chains of the step do not depend on each other: the position encoder of a decoder layer needs only the
+    # reference points (not the self-attention result), the radar encoders need only the radar tokens, and the
+    # classification and regression heads of a radar layer both start from the same activations.  Most GEMMs of this
+    # path fill only part of the GPU (57-228 CTAs of one tile each), so such chains are issued on side streams; under
+    # CUDA-graph capture they become parallel branches that the hardware overlaps.
+    class _Branch:
+        def __init__(self, eng, k):
+            self.eng, self.k, self.ctx = eng, k, None
+
+        def __enter__(self):
+            eng = self.eng
+            if not eng.use_branches:
+                return self
+            if eng._side is None:
+                eng._side = [torch.cuda.Stream(device=eng.device) for _ in range(2)]
+            side = eng._side[self.k]
+            side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            if self.ctx is not None:
+                self.ctx.__exit__(*exc)
+            return False
+
+    def _branch(self, k=0):
+        return FusionDecoderEngine._Branch(self, k)
+
+    def _join(self, k, *tensors):
+        """Make the current stream wait for side stream k; `tensors` were produced there and are used from here on."""
+        if self.use_branches and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side[k])
+        self._keep.extend(t for t in tensors if t is not None)
 
     # ------------------------------------------------------------------ helpers
     def _lin(self, x, key, **kw):
@@ -146,6 +185,15 @@ class FusionDecoderEngine:
         code = None
         for l in range(self.L):
             p = f"transformer.decoder.layers.{l}."
+            # --- branch: position encoder of the cross-attention (T:377) - needs the reference points only
+            with self._branch(0):
+                pe, pe16 = ops.point_embed(ref, self.f32[p + "attentions.1.position_encoder.0.weight"],
+                                           self.f32[p + "attentions.1.position_encoder.0.bias"],
+                                           *self._ln(p + "attentions.1.position_encoder.1"), logit_input=True,
+                                           want_f32=not self.bf16, want_bf16=self.bf16)
+                pos_feat = self._lin(pe16 if self.bf16 else pe, p + "attentions.1.position_encoder.3",
+                                     ln=self._ln(p + "attentions.1.position_encoder.4"), relu=True)
+                self._keep.extend((pe, pe16))
             # --- self attention (mmcv MultiheadAttention wrapper around nn.MultiheadAttention)
             qkv = self._in_proj(x16, p + "attentions.0.attn", self.row_bias_qkv[l])
             qkv3 = qkv.view(B, Q, 3 * C)
@@ -167,12 +215,9 @@ class FusionDecoderEngine:
                 ev.append((e0, e1))
             if self.keep_cam_masks:
                 self.cam_masks.append(cam_mask)
-            pe, pe16 = ops.point_embed(ref, self.f32[p + "attentions.1.position_encoder.0.weight"],
-                                       self.f32[p + "attentions.1.position_encoder.0.bias"],
-                                       *self._ln(p + "attentions.1.position_encoder.1"), logit_input=True,
-                                       want_f32=not self.bf16, want_bf16=self.bf16)
-            pos_feat = self._lin(pe16 if self.bf16 else pe, p + "attentions.1.position_encoder.3",
-                                 ln=self._ln(p + "attentions.1.position_encoder.4"), relu=True)
+            if l == max(self.L - 2, 0):
+                self._start_radar_branch()
+            self._join(0, pos_feat)
             x32, x16 = self._lin(s.view(M, C), p + "attentions.1.output_proj", both=True,
                                  residual=x32, residual2=pos_feat, ln=self._ln(p + "norms.1"))
             # --- FFN (mmcv FFN: x + W2 relu(W1 x)) + norm
@@ -224,12 +269,28 @@ class FusionDecoderEngine:
         kv = self._lin(f, "radar_feat_encoder.4", feed=True, relu=True, post_add=pos)      # H:536
         return kv
 
-    def radar_layers(self, x32, x16, ref, code, tokens, key_xy, B):
-        Q, C, M = self.Q, self.C, B * self.Q
+    def radar_kv(self, tokens, B):
+        """Radar encoders + the K/V projections of all three radar layers (one stacked GEMM): depends on the radar
+        tokens only, so the whole chain runs beside the decoder."""
         R = tokens.shape[1]
         kvfeat = self.radar_encode(tokens, B)                                               # [BR,C]
         o32, o16 = ops.linear(kvfeat, self.radar_wkv, self.radar_bkv, want_f32=not self.bf16, want_bf16=self.bf16)
-        KV = (o16 if self.bf16 else o32).view(B, R, 6 * C)
+        self._keep.append(kvfeat)
+        return (o16 if self.bf16 else o32).view(B, R, 6 * self.C)
+
+    def _start_radar_branch(self):
+        """Radar encoders + K/V projections on side stream 1.  Started right after the sampling launch of the
+        second-to-last decoder layer: the chain (~0.1 ms) then overlaps that layer's tail and the next layer's
+        self-attention, and stays clear of the bandwidth-bound sampling kernels (which own every SM)."""
+        job = getattr(self, "_radar_job", None)
+        if job is None:
+            return
+        self._radar_job = None
+        with self._branch(1):
+            self._radar_kv = self.radar_kv(*job)
+
+    def radar_layers(self, x32, x16, ref, code, KV, key_xy, B):
+        Q, C, M = self.Q, self.C, B * self.Q
         cls_all = torch.empty((3, B, Q, 10), device=self.device, dtype=torch.float32)
         reg_all = torch.empty((3, B, Q, 10), device=self.device, dtype=torch.float32)
         anchor, centre_norm = ref, True
@@ -249,10 +310,12 @@ class FusionDecoderEngine:
                                  row_gate=row_any.view(M), residual=x32, ln=self._ln("rf_norm2" + s))
             h = self._lin(x16, "rf_linear1" + s, feed=True, relu=True)
             x32, x16 = self._lin(h, "rf_linear2" + s, both=True, residual=x32, ln=self._ln("rf_norm3" + s))
-            c = self._lin(x16, "final_cls" + m + ".0", feed=True, ln=self._ln("final_cls" + m + ".1"), relu=True)
-            c = self._lin(c, "final_cls" + m + ".3", feed=True, ln=self._ln("final_cls" + m + ".4"), relu=True)
-            ops.linear(c, self.w["final_cls" + m + ".6.weight"], self.f32["final_cls" + m + ".6.bias"],
-                       out_f32=cls_all[li].view(M, 10))
+            with self._branch(0):      # classification head: independent of the regression head and of the next layer
+                c = self._lin(x16, "final_cls" + m + ".0", feed=True, ln=self._ln("final_cls" + m + ".1"), relu=True)
+                c2 = self._lin(c, "final_cls" + m + ".3", feed=True, ln=self._ln("final_cls" + m + ".4"), relu=True)
+                ops.linear(c2, self.w["final_cls" + m + ".6.weight"], self.f32["final_cls" + m + ".6.bias"],
+                           out_f32=cls_all[li].view(M, 10))
+                self._keep.extend((c, c2, x16))
             g = self._lin(x16, "final_reg" + m + ".0", feed=True, relu=True)
             g = self._lin(g, "final_reg" + m + ".2", feed=True, relu=True)
             reg = reg_all[li].view(M, 10)
@@ -264,6 +327,7 @@ class FusionDecoderEngine:
             aux[f"radar{li}.row_any"] = row_any
             aux[f"radar{li}.geom"] = geom
             anchor, code, centre_norm = reg, reg, False
+        self._join(0, cls_all)
         return cls_all, reg_all, aux
 
     # ------------------------------------------------------------------ whole head (a8)
@@ -283,8 +347,15 @@ class FusionDecoderEngine:
     def _forward_eager(self, prepared, return_aux=False):
         feats, l2i, img_w, img_h, tokens, key_xy = prepared
         B = feats[0].shape[0]
+        self._keep = []
+        self._radar_job = (tokens, B) if self.has_radar else None
+        self._radar_kv = None
         hs, refs, x32, x16, ref, code = self.decoder(feats, l2i, img_w, img_h, B, keep_all=return_aux)
-        cls_all, reg_all, aux = self.radar_layers(x32, x16, ref, code, tokens, key_xy, B)
+        self._start_radar_branch()                 # no-op when the decoder already started it
+        KV = self._radar_kv
+        self._join(1, KV)
+        cls_all, reg_all, aux = self.radar_layers(x32, x16, ref, code, KV, key_xy, B)
+        self._keep = []
         out = dict(all_cls_scores=cls_all, all_bbox_preds=reg_all, enc_cls_scores=None, enc_bbox_preds=None)
         if return_aux:
             aux["hs"] = hs

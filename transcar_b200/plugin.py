@@ -320,6 +320,7 @@ class Detr3DTransformer(nn.Module):
         B = mlvl_feats[0].shape[0]
         feats, l2i, img_w, img_h, _, _ = eng.prepare_inputs(mlvl_feats, kwargs["img_metas"])
         hs, refs, *_ = eng.decoder(feats, l2i, img_w, img_h, B, keep_all=True)
+        eng._keep = []
         Q, C = eng.Q, eng.C
         inter_states = torch.stack([h.view(B, Q, C).permute(1, 0, 2) for h in hs])
         inter_refs = torch.stack([r.view(B, Q, 3) for r in refs])
