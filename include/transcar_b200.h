@@ -34,7 +34,7 @@ extern "C" {
 #define TC_API
 #endif
 
-#define TC_ABI_VERSION 2
+#define TC_ABI_VERSION 3
 #define TC_MAX_LEVELS 4
 #define TC_MAX_CAMS 8
 
@@ -237,6 +237,63 @@ typedef struct {
 } tc_decode_args;
 TC_API int64_t tc_decode_workspace_bytes(int32_t B, int32_t Q, int32_t classes);
 TC_API int tc_decode(const tc_decode_args* a, tc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training variant: backward building blocks of the radar fusion head - the part of TransCAR that trains
+ * (tools/train.py:238-252 freezes backbone, neck, DETR3D transformer, cls/reg branches and query embedding, so
+ * gradients flow through H:531-536 and H:573-729 only).  The backward GEMMs are tc_linear calls on transposed
+ * operands (dX = dY W: A = dY, W = W^T;  dW = dY^T X: A = dY^T, W = X^T); everything else is below.  Gradients that
+ * are reductions (bias / LayerNorm parameters, dK / dV rows shared by many queries) are ACCUMULATED with fp32
+ * atomics: the caller zeroes its gradient bucket once per step.
+ */
+/* dst[c, r] = src[r, c]; dtypes fp32 or bf16 on either side (ld in elements). */
+TC_API int tc_transpose(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst,
+                 int32_t rows, int32_t cols, tc_stream_t stream);
+/* out[n] += sum_m x[m, n]   (bias gradient). */
+TC_API int tc_colsum(const void* x, int32_t dtype, int64_t ldx, int32_t M, int32_t N, float* out, tc_stream_t stream);
+
+/* y = LayerNorm_N(x) * gamma + beta (biased variance, eps), optional ReLU; saves mean / rstd for the backward.
+ * Replaces nn.LayerNorm where the training forward keeps it un-fused (rf_norm2/3*, final_cls*.1/.4,
+ * radar_position_encoder.1/.4). */
+typedef struct {
+  const float* x; int64_t ldx; int32_t M, N;
+  const float* gamma; const float* beta; float eps; int32_t relu;
+  float* y_f32; void* y_bf16; int64_t ldy;       /* either output may be NULL */
+  float* mean; float* rstd;                      /* [M], may be NULL */
+} tc_layernorm_args;
+TC_API int tc_layernorm_fwd(const tc_layernorm_args* a, tc_stream_t stream);
+
+/* dx = LayerNorm backward of dy (+ add, the gradient arriving through a residual connection);
+ * dgamma[n] += sum_m dy * xhat, dbeta[n] += sum_m dy. */
+typedef struct {
+  const float* dy; int64_t ld_dy;
+  const float* x; int64_t ldx;
+  const float* mean; const float* rstd; const float* gamma;
+  int32_t M, N;
+  const float* add; int64_t ld_add;              /* optional */
+  float* dx; int64_t ld_dx;
+  float* dgamma; float* dbeta;                   /* optional, accumulated */
+} tc_layernorm_bwd_args;
+TC_API int tc_layernorm_bwd(const tc_layernorm_bwd_args* a, tc_stream_t stream);
+
+/* dz = dy * (y > 0 if y) * (gate[m] != 0 if gate): ReLU backward and / or the attention row gate (quirk Q6). */
+TC_API int tc_mask_grad(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, const uint8_t* gate, float* dz,
+                 int64_t ld_dz, int32_t M, int32_t N, tc_stream_t stream);
+
+/* Backward of the masked radar attention core (H:578) for fp32 operands: dq is written, dk / dv are accumulated
+ * (one radar point is attended by several queries).  Same key scan and bit-exact mask as the forward sparse kernel;
+ * the softmax is recomputed, nothing but q, k, v needs to be kept from the forward. */
+typedef struct {
+  const float* q; const float* k; const float* v; const float* dout;
+  int64_t ldq, ldk, ldv, ld_dout;
+  int64_t q_batch_stride, k_batch_stride, v_batch_stride;
+  int32_t B, Lq, Lk, heads, D;
+  float scale;
+  const float* geom; const float* key_xy;
+  float* dq; int64_t ld_dq;                      /* [B*Lq, heads*D] */
+  float* dk; float* dv; int64_t ld_dk, ld_dv, dk_batch_stride, dv_batch_stride;
+} tc_attention_bwd_args;
+TC_API int tc_attention_sparse_bwd(const tc_attention_bwd_args* a, tc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtranscar_b200.so")
 
 TC_F32, TC_BF16 = 0, 1
 TC_MAX_LEVELS, TC_MAX_CAMS = 4, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 TC_ATTN_AUTO, TC_ATTN_TENSOR, TC_ATTN_SIMT, TC_ATTN_SPARSE = 0, 1, 2, 3
 
 _vp, _i32, _i64, _f32, _u8p = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -79,6 +79,33 @@ class DecodeArgs(C.Structure):
                 ("workspace", _vp)]
 
 
+class LayerNormArgs(C.Structure):
+    _fields_ = [("x", _vp), ("ldx", _i64), ("M", _i32), ("N", _i32),
+                ("gamma", _vp), ("beta", _vp), ("eps", _f32), ("relu", _i32),
+                ("y_f32", _vp), ("y_bf16", _vp), ("ldy", _i64),
+                ("mean", _vp), ("rstd", _vp)]
+
+
+class LayerNormBwdArgs(C.Structure):
+    _fields_ = [("dy", _vp), ("ld_dy", _i64), ("x", _vp), ("ldx", _i64),
+                ("mean", _vp), ("rstd", _vp), ("gamma", _vp),
+                ("M", _i32), ("N", _i32),
+                ("add", _vp), ("ld_add", _i64),
+                ("dx", _vp), ("ld_dx", _i64),
+                ("dgamma", _vp), ("dbeta", _vp)]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("dout", _vp),
+                ("ldq", _i64), ("ldk", _i64), ("ldv", _i64), ("ld_dout", _i64),
+                ("q_batch_stride", _i64), ("k_batch_stride", _i64), ("v_batch_stride", _i64),
+                ("B", _i32), ("Lq", _i32), ("Lk", _i32), ("heads", _i32), ("D", _i32),
+                ("scale", _f32),
+                ("geom", _vp), ("key_xy", _vp),
+                ("dq", _vp), ("ld_dq", _i64),
+                ("dk", _vp), ("dv", _vp), ("ld_dk", _i64), ("ld_dv", _i64), ("dk_batch_stride", _i64), ("dv_batch_stride", _i64)]
+
+
 # every symbol include/transcar_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "tc_abi_version": (C.c_int, []),
@@ -97,6 +124,12 @@ SYMBOLS = {
     "tc_cast_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "tc_decode_workspace_bytes": (C.c_int64, [_i32, _i32, _i32]),
     "tc_decode": (C.c_int, [C.POINTER(DecodeArgs), _vp]),
+    "tc_transpose": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _vp]),
+    "tc_colsum": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    "tc_layernorm_fwd": (C.c_int, [C.POINTER(LayerNormArgs), _vp]),
+    "tc_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdArgs), _vp]),
+    "tc_mask_grad": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "tc_attention_sparse_bwd": (C.c_int, [C.POINTER(AttentionBwdArgs), _vp]),
 }
 
 _lib = None

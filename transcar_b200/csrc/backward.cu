@@ -1,0 +1,402 @@
+// Backward-pass building blocks of the radar fusion head (the part of TransCAR that trains: tools/train.py:238-252
+// freezes the backbone, neck, DETR3D transformer, cls/reg branches and query embedding).  The GEMMs of the backward
+// pass are tc_linear calls on transposed operands (dX = dY W, dW = dY^T X); this file holds everything else:
+//   tc_transpose        [R,C] -> [C,R] with optional fp32 -> bf16 conversion (operands of the wgrad GEMMs, W^T)
+//   tc_colsum           out[n] += sum_m x[m,n]                               (bias gradients)
+//   tc_layernorm_fwd    y = LN(x) * gamma + beta, saves mean / rstd          (training forward keeps LN un-fused)
+//   tc_layernorm_bwd    dx (+= add), dgamma += , dbeta +=                    (nn.LayerNorm backward, biased variance)
+//   tc_mask_grad        dz = dy * (y > 0) * gate[row]                        (ReLU backward and / or the row gate of quirk Q6)
+//   tc_attention_sparse_bwd   dq, dk +=, dv += of the masked radar attention (detr3d_head.py:578), same key scan and
+//                       bit-exact mask as attention_sparse.cu; the softmax is recomputed, never stored
+// All reductions into parameters / shared rows use fp32 atomics (the caller zeroes the gradient bucket once per step).
+#include "tc_common.cuh"
+
+namespace tc {
+namespace {
+
+// ---- transpose ---------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ src, long long ld_src, TO* __restrict__ dst,
+                                                        long long ld_dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  pdl_trigger();
+  pdl_wait();
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? static_cast<float>(src[(long long)r * ld_src + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;                         // dst[c][r]
+    if (c < cols && r < rows) dst[(long long)c * ld_dst + r] = static_cast<TO>(tile[tx][i]);
+  }
+}
+
+// ---- column sum --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx, int M, int N, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  pdl_trigger();
+  pdl_wait();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (n < N)
+    for (int m = blockIdx.y * 8 + ty; m < M; m += gridDim.y * 8) s += static_cast<float>(x[(long long)m * ldx + n]);
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += part[i][tx];
+    atomicAdd(out + n, s);
+  }
+}
+
+// ---- LayerNorm ---------------------------------------------------------------------------------------------
+constexpr int kLnMaxPerLane = 32;      // N <= 1024
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const tc_layernorm_args a) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= a.M) return;
+  const float* x = a.x + (long long)m * a.ldx;
+  const int per = (a.N + 31) >> 5;
+  float v[kLnMaxPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxPerLane; ++j) {
+    v[j] = 0.f;
+    if (j < per) {
+      const int n = j * 32 + lane;
+      if (n < a.N) { v[j] = x[n]; s += v[j]; }
+    }
+  }
+  const float mean = warp_sum(s) / (float)a.N;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxPerLane; ++j)
+    if (j < per && j * 32 + lane < a.N) { const float d = v[j] - mean; sq += d * d; }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)a.N + a.eps);
+  if (lane == 0) {
+    if (a.mean) a.mean[m] = mean;
+    if (a.rstd) a.rstd[m] = rstd;
+  }
+#pragma unroll
+  for (int j = 0; j < kLnMaxPerLane; ++j) {
+    if (j < per) {
+      const int n = j * 32 + lane;
+      if (n < a.N) {
+        float y = (v[j] - mean) * rstd * a.gamma[n] + a.beta[n];
+        if (a.relu) y = fmaxf(y, 0.f);
+        if (a.y_f32) a.y_f32[(long long)m * a.ldy + n] = y;
+        if (a.y_bf16) static_cast<__nv_bfloat16*>(a.y_bf16)[(long long)m * a.ldy + n] = __float2bfloat16_rn(y);
+      }
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum_m dy * xhat;  dbeta += sum_m dy
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const tc_layernorm_bwd_args a) {
+  extern __shared__ float sh[];                     // [2][N] per-CTA partial dgamma / dbeta
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 2 * a.N; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int per = (a.N + 31) >> 5;
+  for (int m = blockIdx.x * 8 + warp; m < a.M; m += gridDim.x * 8) {
+    const float* x = a.x + (long long)m * a.ldx;
+    const float* dy = a.dy + (long long)m * a.ld_dy;
+    const float mean = a.mean[m], rstd = a.rstd[m];
+    float xh[kLnMaxPerLane], g[kLnMaxPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxPerLane; ++j) {
+      xh[j] = 0.f; g[j] = 0.f;
+      if (j < per) {
+        const int n = j * 32 + lane;
+        if (n < a.N) {
+          const float d = dy[n];
+          xh[j] = (x[n] - mean) * rstd;
+          g[j] = d * a.gamma[n];
+          s1 += g[j];
+          s2 = fmaf(g[j], xh[j], s2);
+          atomicAdd(&sh[n], d * xh[j]);              // shared-memory atomics: 8 warps of the CTA hit distinct rows
+          atomicAdd(&sh[a.N + n], d);
+        }
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)a.N, m2 = warp_sum(s2) / (float)a.N;
+#pragma unroll
+    for (int j = 0; j < kLnMaxPerLane; ++j) {
+      if (j < per) {
+        const int n = j * 32 + lane;
+        if (n < a.N) {
+          float v = rstd * (g[j] - m1 - xh[j] * m2);
+          if (a.add) v += a.add[(long long)m * a.ld_add + n];
+          a.dx[(long long)m * a.ld_dx + n] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
+    if (a.dgamma) atomicAdd(a.dgamma + n, sh[n]);
+    if (a.dbeta) atomicAdd(a.dbeta + n, sh[a.N + n]);
+  }
+}
+
+// ---- ReLU backward / row gate ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_grad_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ y,
+                                                        long long ld_y, const uint8_t* __restrict__ gate, float* __restrict__ dz,
+                                                        long long ld_dz, int M, int N) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  float v = dy[(long long)m * ld_dy + n];
+  if (y && !(y[(long long)m * ld_y + n] > 0.f)) v = 0.f;
+  if (gate && gate[m] == 0) v = 0.f;
+  dz[(long long)m * ld_dz + n] = v;
+}
+
+// ---- masked radar attention backward ---------------------------------------------------------------------------------
+constexpr int kWarps = 8;
+constexpr int kKeyTile = 2048;
+
+struct SparseBwdParams {
+  const float* q; const float* k; const float* v; const float* dout;
+  long long ldq, ldk, ldv, ldo, qbs, kbs, vbs;
+  int B, Lq, Lk;
+  float scale;
+  const float* geom; const float* key_xy;
+  float* dq; long long ld_dq;
+  float* dk; float* dv; long long ld_dk, ld_dv, dkbs, dvbs;
+};
+
+__device__ __forceinline__ void ld8(const float* p, float (&d)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+
+// One warp per (sample, query); lane owns 8 channels, a head = 4 lanes (see attention_sparse.cu).  Two passes over the
+// allowed keys: (1) row max and normaliser per head, (2) p, dP = dO.v, dS = p (dP - dO.O), accumulate dq / dk / dv.
+__global__ void __launch_bounds__(kWarps * 32) attention_sparse_bwd_kernel(const SparseBwdParams p) {
+  __shared__ float s_kx[kKeyTile], s_ky[kKeyTile], s_kn[kKeyTile];
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  const bool active = q < p.Lq;
+  const long long row = (long long)b * p.Lq + (active ? q : 0);
+  const float* g = p.geom + row * 8;
+  const float cx = __ldg(g + 0), cy = __ldg(g + 1), fx = __ldg(g + 2), fy = __ldg(g + 3);
+  const float rx = __ldg(g + 4), ry = __ldg(g + 5), radius = __ldg(g + 6);
+  const Circle cc = make_circle(cx, cy), cf = make_circle(fx, fy), cr = make_circle(rx, ry);
+  const float span = fmaxf(sqrtf((fx - cx) * (fx - cx) + (fy - cy) * (fy - cy)),
+                           sqrtf((rx - cx) * (rx - cx) + (ry - cy) * (ry - cy)));
+  const float bound = radius + span + 0.25f;
+  const float bound2 = bound * bound;
+
+  float qv[8], dO[8], dq[8];
+  ld8(p.q + (long long)b * p.qbs + (long long)(active ? q : 0) * p.ldq + lane * 8, qv);
+  ld8(p.dout + row * p.ldo + lane * 8, dO);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { qv[i] *= p.scale; dq[i] = 0.f; }
+  const float2* keys = reinterpret_cast<const float2*>(p.key_xy) + (long long)b * p.Lk;
+
+  float m_run = -INFINITY, l_run = 0.f;                   // per head: running max and normaliser
+  float oacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oacc[i] = 0.f;
+
+  bool live = active;
+  for (int pass = 0; pass < 2; ++pass) {
+    float inv_l = 0.f, D = 0.f;
+    if (pass == 1 && !(l_run > 0.f)) live = false;          // no allowed key: all gradients of this row are zero
+    if (pass == 1 && live) {                                // (the warp keeps taking part in the block barriers below)
+      inv_l = 1.0f / l_run;
+      // D = dO . O per head, O = oacc / l
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t = fmaf(dO[i], oacc[i] * inv_l, t);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      D = t;
+    }
+    for (int t0 = 0; t0 < p.Lk; t0 += kKeyTile) {
+      const int nt = min(kKeyTile, p.Lk - t0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nt; i += kWarps * 32) {
+        const float2 xy = __ldg(keys + t0 + i);
+        s_kx[i] = xy.x; s_ky[i] = xy.y; s_kn[i] = key_norm(xy.x, xy.y);
+      }
+      __syncthreads();
+      if (!live) continue;
+      for (int k0 = 0; k0 < nt; k0 += 32) {
+        const int key = k0 + lane;
+        float kx = 0.f, ky = 0.f;
+        bool cand = false;
+        if (key < nt) {
+          kx = s_kx[key]; ky = s_ky[key];
+          const float dx = kx - cx, dy = ky - cy;
+          cand = !(fmaf(dx, dx, dy * dy) >= bound2);
+        }
+        if (!__any_sync(0xffffffffu, cand)) continue;
+        bool ok = false;
+        if (cand) ok = radar_allowed(cc, cf, cr, radius, kx, ky, s_kn[key]);
+        unsigned todo = __ballot_sync(0xffffffffu, ok);
+        while (todo) {
+          const int j = t0 + k0 + __ffs(todo) - 1;
+          todo &= todo - 1;
+          float kv[8], vv[8];
+          ld8(p.k + (long long)b * p.kbs + (long long)j * p.ldk + lane * 8, kv);
+          ld8(p.v + (long long)b * p.vbs + (long long)j * p.ldv + lane * 8, vv);
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s = fmaf(qv[i], kv[i], s);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          if (pass == 0) {
+            const float m_new = fmaxf(m_run, s);
+            const float corr = expf(m_run - m_new);
+            const float pj = expf(s - m_new);
+            l_run = fmaf(l_run, corr, pj);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) oacc[i] = fmaf(oacc[i], corr, pj * vv[i]);
+            m_run = m_new;
+          } else {
+            const float pj = expf(s - m_run) * inv_l;
+            float dP = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dP = fmaf(dO[i], vv[i], dP);
+            dP += __shfl_xor_sync(0xffffffffu, dP, 1);
+            dP += __shfl_xor_sync(0xffffffffu, dP, 2);
+            const float dS = pj * (dP - D);
+            float* dkr = p.dk + (long long)b * p.dkbs + (long long)j * p.ld_dk + lane * 8;
+            float* dvr = p.dv + (long long)b * p.dvbs + (long long)j * p.ld_dv + lane * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              dq[i] = fmaf(dS, kv[i], dq[i]);
+              atomicAdd(dkr + i, dS * qv[i]);              // qv already carries the 1/sqrt(d) scale
+              atomicAdd(dvr + i, pj * dO[i]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!active) return;
+  float4* o = reinterpret_cast<float4*>(p.dq + row * p.ld_dq + lane * 8);
+  o[0] = make_float4(dq[0] * p.scale, dq[1] * p.scale, dq[2] * p.scale, dq[3] * p.scale);
+  o[1] = make_float4(dq[4] * p.scale, dq[5] * p.scale, dq[6] * p.scale, dq[7] * p.scale);
+}
+
+}  // namespace
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int tc_transpose(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst,
+                            int32_t rows, int32_t cols, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(src && dst, TC_ERR_NULL, "tc_transpose: NULL pointer");
+  TC_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= rows, TC_ERR_SHAPE, "tc_transpose: bad shape");
+  TC_REQUIRE((src_dtype == TC_F32 || src_dtype == TC_BF16) && (dst_dtype == TC_F32 || dst_dtype == TC_BF16), TC_ERR_DTYPE,
+             "tc_transpose: bad dtype");
+  if (rows == 0 || cols == 0) return TC_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  cudaStream_t s = as_stream(stream);
+  const bool si = src_dtype == TC_BF16, di = dst_dtype == TC_BF16;
+  if (!si && !di) launch(transpose_kernel<float, float>, grid, dim3(256), 0, s, 1u, (const float*)src, (long long)ld_src, (float*)dst, (long long)ld_dst, rows, cols);
+  else if (!si && di) launch(transpose_kernel<float, __nv_bfloat16>, grid, dim3(256), 0, s, 1u, (const float*)src, (long long)ld_src, (__nv_bfloat16*)dst, (long long)ld_dst, rows, cols);
+  else if (si && !di) launch(transpose_kernel<__nv_bfloat16, float>, grid, dim3(256), 0, s, 1u, (const __nv_bfloat16*)src, (long long)ld_src, (float*)dst, (long long)ld_dst, rows, cols);
+  else launch(transpose_kernel<__nv_bfloat16, __nv_bfloat16>, grid, dim3(256), 0, s, 1u, (const __nv_bfloat16*)src, (long long)ld_src, (__nv_bfloat16*)dst, (long long)ld_dst, rows, cols);
+  count_launch();
+  return check_launch("tc_transpose");
+}
+
+extern "C" int tc_colsum(const void* x, int32_t dtype, int64_t ldx, int32_t M, int32_t N, float* out, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(x && out, TC_ERR_NULL, "tc_colsum: NULL pointer");
+  TC_REQUIRE(M >= 0 && N > 0 && ldx >= N, TC_ERR_SHAPE, "tc_colsum: bad shape");
+  TC_REQUIRE(dtype == TC_F32 || dtype == TC_BF16, TC_ERR_DTYPE, "tc_colsum: bad dtype");
+  if (M == 0) return TC_OK;
+  int slices = (M + 255) / 256;
+  if (slices > 64) slices = 64;
+  dim3 grid((N + 31) / 32, slices);
+  if (dtype == TC_F32) launch(colsum_kernel<float>, grid, dim3(256), 0, as_stream(stream), 1u, (const float*)x, (long long)ldx, M, N, out);
+  else launch(colsum_kernel<__nv_bfloat16>, grid, dim3(256), 0, as_stream(stream), 1u, (const __nv_bfloat16*)x, (long long)ldx, M, N, out);
+  count_launch();
+  return check_launch("tc_colsum");
+}
+
+extern "C" int tc_layernorm_fwd(const tc_layernorm_args* a, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_layernorm_fwd: args is NULL");
+  TC_REQUIRE(a->x && a->gamma && a->beta && (a->y_f32 || a->y_bf16), TC_ERR_NULL, "tc_layernorm_fwd: NULL pointer");
+  TC_REQUIRE(a->M >= 0 && a->N > 0 && a->N <= 32 * kLnMaxPerLane && a->ldx >= a->N && a->ldy >= a->N, TC_ERR_SHAPE,
+             "tc_layernorm_fwd: bad shape");
+  if (a->M == 0) return TC_OK;
+  launch(layernorm_fwd_kernel, dim3((a->M + 7) / 8), dim3(256), 0, as_stream(stream), 1u, *a);
+  count_launch();
+  return check_launch("tc_layernorm_fwd");
+}
+
+extern "C" int tc_layernorm_bwd(const tc_layernorm_bwd_args* a, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_layernorm_bwd: args is NULL");
+  TC_REQUIRE(a->dy && a->x && a->mean && a->rstd && a->gamma && a->dx, TC_ERR_NULL, "tc_layernorm_bwd: NULL pointer");
+  TC_REQUIRE(a->M >= 0 && a->N > 0 && a->N <= 32 * kLnMaxPerLane, TC_ERR_SHAPE, "tc_layernorm_bwd: bad shape");
+  if (a->M == 0) return TC_OK;
+  int ctas = (a->M + 7) / 8;
+  if (ctas > 296) ctas = 296;
+  launch(layernorm_bwd_kernel, dim3(ctas), dim3(256), (size_t)2 * a->N * sizeof(float), as_stream(stream), 1u, *a);
+  count_launch();
+  return check_launch("tc_layernorm_bwd");
+}
+
+extern "C" int tc_mask_grad(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, const uint8_t* gate, float* dz,
+                            int64_t ld_dz, int32_t M, int32_t N, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(dy && dz, TC_ERR_NULL, "tc_mask_grad: NULL pointer");
+  TC_REQUIRE(M >= 0 && N > 0, TC_ERR_SHAPE, "tc_mask_grad: bad shape");
+  if (M == 0) return TC_OK;
+  const long long n = (long long)M * N;
+  launch(mask_grad_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, as_stream(stream), 1u, dy, (long long)ld_dy, y,
+         (long long)ld_y, gate, dz, (long long)ld_dz, M, N);
+  count_launch();
+  return check_launch("tc_mask_grad");
+}
+
+extern "C" int tc_attention_sparse_bwd(const tc_attention_bwd_args* a, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_attention_sparse_bwd: args is NULL");
+  TC_REQUIRE(a->q && a->k && a->v && a->dout && a->geom && a->key_xy && a->dq && a->dk && a->dv, TC_ERR_NULL,
+             "tc_attention_sparse_bwd: NULL pointer");
+  TC_REQUIRE(a->heads == 8 && a->D == 32, TC_ERR_SHAPE, "tc_attention_sparse_bwd: needs 8 heads x 32");
+  TC_REQUIRE(a->B >= 0 && a->Lq >= 0 && a->Lk >= 0 && a->B <= 65535, TC_ERR_SHAPE, "tc_attention_sparse_bwd: bad shape");
+  TC_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->dout) && aligned16(a->dq) &&
+                 a->ldq % 4 == 0 && a->ldk % 4 == 0 && a->ldv % 4 == 0 && a->ld_dout % 4 == 0 && a->ld_dq % 4 == 0 &&
+                 a->q_batch_stride % 4 == 0 && a->k_batch_stride % 4 == 0 && a->v_batch_stride % 4 == 0,
+             TC_ERR_ALIGN, "tc_attention_sparse_bwd: rows must be 16-byte aligned");
+  if (a->B == 0 || a->Lq == 0) return TC_OK;
+  SparseBwdParams p;
+  p.q = a->q; p.k = a->k; p.v = a->v; p.dout = a->dout;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.ldo = a->ld_dout;
+  p.qbs = a->q_batch_stride; p.kbs = a->k_batch_stride; p.vbs = a->v_batch_stride;
+  p.B = a->B; p.Lq = a->Lq; p.Lk = a->Lk; p.scale = a->scale;
+  p.geom = a->geom; p.key_xy = a->key_xy;
+  p.dq = a->dq; p.ld_dq = a->ld_dq;
+  p.dk = a->dk; p.dv = a->dv; p.ld_dk = a->ld_dk; p.ld_dv = a->ld_dv;
+  p.dkbs = a->dk_batch_stride; p.dvbs = a->dv_batch_stride;
+  dim3 grid((a->Lq + kWarps - 1) / kWarps, a->B);
+  launch(attention_sparse_bwd_kernel, grid, dim3(kWarps * 32), 0, as_stream(stream), 1u, p);
+  count_launch();
+  return check_launch("tc_attention_sparse_bwd");
+}

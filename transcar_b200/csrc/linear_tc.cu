@@ -127,7 +127,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int num_kb = p.K / BK;
+  const int num_kb = (p.K + BK - 1) / BK;      // a partial last K block is zero-filled by TMA (both operands)
   pdl_trigger();
 
   if (threadIdx.x == 0) {
@@ -470,7 +470,7 @@ bool linear_tc_supported(const tc_linear_args* a) {
   static const bool disabled = getenv("TC_DISABLE_TC_LINEAR") != nullptr;        // debugging / A-B measurements
   if (disabled) return false;
   if (a->a_dtype != TC_BF16 || a->w_dtype != TC_BF16) return false;
-  if (a->K % BK != 0 || a->K < BK) return false;
+  if (a->K % 8 != 0 || a->K < BK) return false;       // 16-byte row pitch; a partial last K block is zero-filled
   // fused LayerNorm: the row block's CTAs form one cluster (portable size <= 8) -> N = 64, 128 or 256 here
   if (a->ln_gamma && !(a->N == 64 || a->N == 128 || a->N == 256)) return false;
   // TMA: 16-byte aligned base and row pitch for both operands

@@ -320,3 +320,105 @@ def decode(cls, code, max_num, post_center_range):
     a.boxes, a.scores, a.labels, a.keep = boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), keep.data_ptr()
     _lib.check(lib.tc_decode(C.byref(a), _stream()), "decode")
     return boxes, scores, labels, keep
+
+
+# --------------------------------------------------------------------------------------- backward building blocks
+def transpose(src, out_dtype=None, out=None):
+    """[R,C] -> [C,R] (fp32 / bf16 on either side)."""
+    lib = _lib.load()
+    s2, lds = _rows(_need(src, "src"), "src")
+    R, Cc = s2.shape
+    if out is None:
+        out = torch.empty((Cc, R), device=s2.device, dtype=out_dtype or s2.dtype)
+    o2, ldo = _rows(_need(out, "out"), "out")
+    _lib.check(_call("transpose", lib.tc_transpose, _ptr(s2), _DT[s2.dtype], lds, _ptr(o2), _DT[o2.dtype], ldo, R, Cc, _stream()),
+               "transpose")
+    return out
+
+
+def colsum_(x, out):
+    """out[n] += sum_m x[m,n]  (out: fp32 [N], accumulated in place)."""
+    lib = _lib.load()
+    x2, ldx = _rows(_need(x, "x"), "x")
+    _need(out, "out", torch.float32)
+    _lib.check(_call("colsum", lib.tc_colsum, _ptr(x2), _DT[x2.dtype], ldx, x2.shape[0], x2.shape[1], _ptr(out), _stream()), "colsum")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, relu=False, want_bf16=False, save_stats=True):
+    """y = LN(x)*gamma+beta (optional ReLU); returns (y_f32, y_bf16 or None, mean, rstd)."""
+    lib = _lib.load()
+    x2, ldx = _rows(_need(x, "x", torch.float32), "x")
+    M, N = x2.shape
+    y = torch.empty((M, N), device=x2.device, dtype=torch.float32)
+    y16 = torch.empty((M, N), device=x2.device, dtype=torch.bfloat16) if want_bf16 else None
+    mean = torch.empty((M,), device=x2.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty((M,), device=x2.device, dtype=torch.float32) if save_stats else None
+    a = _lib.LayerNormArgs()
+    a.x, a.ldx, a.M, a.N = x2.data_ptr(), ldx, M, N
+    a.gamma, a.beta = _need(gamma, "gamma", torch.float32).data_ptr(), _need(beta, "beta", torch.float32).data_ptr()
+    a.eps, a.relu = float(eps), 1 if relu else 0
+    a.y_f32, a.y_bf16, a.ldy = y.data_ptr(), _ptr(y16), N
+    a.mean, a.rstd = _ptr(mean), _ptr(rstd)
+    _lib.check(_call("layernorm_fwd", lib.tc_layernorm_fwd, C.byref(a), _stream()), "layernorm_fwd")
+    return y, y16, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma=None, dbeta=None, add=None):
+    """dx of LayerNorm (+ add); dgamma / dbeta (fp32 [N]) are accumulated in place."""
+    lib = _lib.load()
+    dy2, ld_dy = _rows(_need(dy, "dy", torch.float32), "dy")
+    x2, ldx = _rows(_need(x, "x", torch.float32), "x")
+    M, N = x2.shape
+    dx = torch.empty((M, N), device=x2.device, dtype=torch.float32)
+    a = _lib.LayerNormBwdArgs()
+    a.dy, a.ld_dy, a.x, a.ldx = dy2.data_ptr(), ld_dy, x2.data_ptr(), ldx
+    a.mean, a.rstd, a.gamma = mean.data_ptr(), rstd.data_ptr(), _need(gamma, "gamma", torch.float32).data_ptr()
+    a.M, a.N = M, N
+    if add is not None:
+        ad, ld_add = _rows(_need(add, "add", torch.float32), "add")
+        a.add, a.ld_add = ad.data_ptr(), ld_add
+    a.dx, a.ld_dx = dx.data_ptr(), N
+    a.dgamma, a.dbeta = _ptr(dgamma), _ptr(dbeta)
+    _lib.check(_call("layernorm_bwd", lib.tc_layernorm_bwd, C.byref(a), _stream()), "layernorm_bwd")
+    return dx
+
+
+def mask_grad(dy, y=None, gate=None):
+    """dy * (y > 0) * gate[row]  -> new fp32 tensor."""
+    lib = _lib.load()
+    dy2, ld_dy = _rows(_need(dy, "dy", torch.float32), "dy")
+    M, N = dy2.shape
+    dz = torch.empty((M, N), device=dy2.device, dtype=torch.float32)
+    y_ptr, ld_y = None, 0
+    if y is not None:
+        y2, ld_y = _rows(_need(y, "y", torch.float32), "y")
+        y_ptr = _ptr(y2)
+    _lib.check(_call("mask_grad", lib.tc_mask_grad, _ptr(dy2), ld_dy, y_ptr, ld_y, _ptr(gate), _ptr(dz), N, M, N, _stream()),
+               "mask_grad")
+    return dz
+
+
+def attention_sparse_bwd(q, k, v, dout, heads, geom, key_xy, dk, dv, scale=None):
+    """Backward of the masked radar attention core (fp32).  q/dout [B,Lq,E]; k/v [B,Lk,E] views; dk/dv are fp32 views of the
+    same shape as k/v and are ACCUMULATED.  Returns dq [B,Lq,E]."""
+    lib = _lib.load()
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    D = E // heads
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (dout, "dout"), (dk, "dk"), (dv, "dv")):
+        _need(t, n, torch.float32)
+    dout = dout.contiguous()
+    dq = torch.empty((B, Lq, E), device=q.device, dtype=torch.float32)
+    a = _lib.AttentionBwdArgs()
+    a.q, a.k, a.v, a.dout = q.data_ptr(), k.data_ptr(), v.data_ptr(), dout.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ld_dout = q.stride(1), k.stride(1), v.stride(1), dout.stride(1)
+    a.q_batch_stride, a.k_batch_stride, a.v_batch_stride = q.stride(0), k.stride(0), v.stride(0)
+    a.B, a.Lq, a.Lk, a.heads, a.D = B, Lq, Lk, heads, D
+    a.scale = float(scale if scale is not None else 1.0 / math.sqrt(D))
+    a.geom, a.key_xy = _need(geom, "geom", torch.float32).contiguous().data_ptr(), _need(key_xy, "key_xy", torch.float32).contiguous().data_ptr()
+    a.dq, a.ld_dq = dq.data_ptr(), E
+    a.dk, a.dv = dk.data_ptr(), dv.data_ptr()
+    a.ld_dk, a.ld_dv, a.dk_batch_stride, a.dv_batch_stride = dk.stride(1), dv.stride(1), dk.stride(0), dv.stride(0)
+    _lib.check(_call("attention_sparse_bwd", lib.tc_attention_sparse_bwd, C.byref(a), _stream()), "attention_sparse_bwd")
+    return dq

@@ -469,8 +469,32 @@ class Detr3DHead(nn.Module):
         return self._engine
 
     def forward(self, mlvl_feats, img_metas, return_aux=False):
-        _no_grad_required(self)
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self.forward_train(mlvl_feats, img_metas)
         return self.engine().forward(mlvl_feats, img_metas, return_aux=return_aux)
+
+    def forward_train(self, mlvl_feats, img_metas):
+        """Training variant (reference recipe ``tools/train.py:238-252``: only the radar head trains).  The frozen DETR3D
+        decoder runs through the inference engine without autograd; the radar head runs through
+        ``transcar_b200.training.RadarHeadTrainer`` (library kernels forward and backward) behind one autograd node, so
+        ``loss.backward()`` fills ``.grad`` of the radar-head parameters.  Dropout (p = 0.1 in the reference configs) is
+        not applied.  Parameters outside the radar head receive no gradient."""
+        from .training import RadarHeadTrainer, radar_head_apply
+        eng = self.engine()
+        with torch.no_grad():
+            feats, l2i, img_w, img_h, tokens, key_xy = eng.prepare_inputs(mlvl_feats, img_metas)
+            B = feats[0].shape[0]
+            eng._keep = []
+            _, _, x32, _, ref, code = eng.decoder(feats, l2i, img_w, img_h, B, keep_all=False)
+            eng._keep = []
+        named = dict(self.named_parameters())
+        key = tuple(p.data_ptr() for p in named.values())
+        if getattr(self, "_trainer", None) is None or self._trainer_key != key:
+            live = {k: v.data for k, v in named.items() if v.dtype == torch.float32}
+            self._trainer = RadarHeadTrainer(live, num_heads=8, pc_range=self.pc_range)
+            self._trainer_key = key
+        cls_all, reg_all = radar_head_apply(self._trainer, named, x32.float(), ref, code, tokens, key_xy, B)
+        return dict(all_cls_scores=cls_all, all_bbox_preds=reg_all, enc_cls_scores=None, enc_bbox_preds=None)
 
     def get_bboxes(self, preds_dicts, img_metas, rescale=False):
         """Reference ``detr3d_head.py:1004-1023``: decode, move z from centre to box bottom, wrap in the

@@ -1,0 +1,239 @@
+"""Training variant of the TransCAR fusion head: forward + backward of everything that trains.
+
+The reference recipe (``tools/train.py:238-252``) freezes the backbone, neck, the DETR3D transformer, ``cls_branches``,
+``reg_branches`` and ``query_embedding``; gradients exist only for the radar head (reference
+``projects/mmdet3d_plugin/models/dense_heads/detr3d_head.py``, H below):
+
+    radar_position_encoder / radar_feat_encoder (H:531-536), rf_multihead_attn{,2,3} (H:578/649/707),
+    rf_linear{1,2}{,_2,_3} + rf_norm{2,3}{,_2,_3} (H:583-586), final_cls{,2,3} / final_reg{,2,3} (H:592-593)
+
+so the decoder runs through the inference engine (no grad) and this module runs the radar head with every intermediate
+kept, then walks it backwards.  All math is library kernels: forward GEMMs ``tc_linear``, LayerNorm ``tc_layernorm_fwd``,
+masked attention ``tc_attention_fwd`` (sparse); backward GEMMs are ``tc_linear`` on transposed operands
+(``dX = dY W`` with the running gradient fused in as the residual, ``dW = dY^T X``), plus ``tc_colsum``,
+``tc_layernorm_bwd``, ``tc_mask_grad`` and ``tc_attention_sparse_bwd``.  Masks are not differentiable; the only cross-layer
+gradient paths are the residual stream and ``reg_l[:, (0,1,4)] += reg_{l-1}[:, (0,1,4)]`` (H:664-665, H:722-723), whose
+backward is one ``tc_box_anchor_add`` on the gradients.  Arithmetic is fp32 (the reference trains this head in fp32).
+
+Data parallel: every rank runs its own samples; ``sharding.GradBucket`` all-reduces the flat gradient buffer once per step.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .engine import RADIUS_CLAMP
+from .radar_tokens import NUM_RADAR_FEATS
+
+_SUF = ("", "_2", "_3")
+_NUM = ("", "2", "3")
+
+
+def trainable_names(state_dict_keys):
+    """Parameter names that train under the reference recipe (and have a gradient path: ``rf_norm1*``,
+    ``attention_weights{2,3}`` and ``output_proj{2,3}`` are never used in forward, H:135,191-195)."""
+    pre = ("radar_position_encoder.", "radar_feat_encoder.", "rf_multihead_attn", "rf_linear", "rf_norm2", "rf_norm3",
+           "final_cls", "final_reg")
+    return [k for k in state_dict_keys if k.startswith(pre)]
+
+
+class RadarHeadTrainer:
+    """fp32 forward/backward of the radar fusion head over batch-major ``[B*Q, C]`` activations."""
+
+    def __init__(self, params, num_heads=8, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)):
+        """``params``: dict name -> fp32 CUDA tensor (the live parameters, reference key names)."""
+        self.p = params
+        self.heads = num_heads
+        self.pc_range = [float(v) for v in pc_range]
+        self.names = trainable_names(params.keys())
+        dev = next(iter(params.values())).device
+        n = sum(params[k].numel() for k in self.names)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.g = {}
+        off = 0
+        for k in self.names:
+            t = params[k]
+            self.g[k] = self.flat_grad[off: off + t.numel()].view_as(t)
+            off += t.numel()
+        self.ctx = None
+
+    # ------------------------------------------------------------------ differentiable pieces (forward records a tape)
+    def _linear(self, tape, x, wkey, bkey, relu=False, residual=None, gate=None, w_rows=None):
+        """y = [relu]( gate * (x W^T + b) + residual ).  ``w_rows`` selects a row range of a packed weight/bias."""
+        W, b = self.p[wkey], self.p[bkey]
+        if w_rows is not None:
+            W, b = W[w_rows[0]:w_rows[1]], b[w_rows[0]:w_rows[1]]
+        y, _ = ops.linear(x, W, b, relu=relu, residual=residual, row_gate=gate)
+        tape.append(("linear", x, wkey, bkey, w_rows, y if relu else None, gate))
+        return y
+
+    def _linear_bwd(self, rec, dy, dx_accum=None, need_dx=True):
+        _, x, wkey, bkey, w_rows, y_relu, gate = rec
+        if y_relu is not None or gate is not None:
+            dy = ops.mask_grad(dy, y=y_relu, gate=gate)
+        W, gW, gb = self.p[wkey], self.g[wkey], self.g[bkey]
+        if w_rows is not None:
+            W, gW, gb = W[w_rows[0]:w_rows[1]], gW[w_rows[0]:w_rows[1]], gb[w_rows[0]:w_rows[1]]
+        ops.colsum_(dy, gb)
+        dyT, xT = ops.transpose(dy), ops.transpose(x)                      # [N,M], [K,M]
+        ops.linear(dyT, xT, None, out_f32=gW)                              # dW = dY^T X
+        if not need_dx:
+            return None
+        WT = ops.transpose(W)                                              # [K,N]
+        dx, _ = ops.linear(dy, WT, None, residual=dx_accum)                # dX = dY W (+ running gradient)
+        return dx
+
+    def _ln(self, tape, x, key, relu=False):
+        y, _, mean, rstd = ops.layernorm_fwd(x, self.p[key + ".weight"], self.p[key + ".bias"], relu=relu)
+        tape.append(("ln", x, key, mean, rstd, y if relu else None))
+        return y
+
+    def _ln_bwd(self, rec, dy, add=None):
+        _, x, key, mean, rstd, y_relu = rec
+        if y_relu is not None:
+            dy = ops.mask_grad(dy, y=y_relu)
+        return ops.layernorm_bwd(dy, x, mean, rstd, self.p[key + ".weight"], dgamma=self.g[key + ".weight"],
+                                 dbeta=self.g[key + ".bias"], add=add)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x0, ref, code, tokens, key_xy, B):
+        """x0 [B*Q,C] decoder output, ref [B*Q,3] refined reference points, code [B*Q,10] = reg_branches[5](x0),
+        tokens [B,R,36], key_xy [B,R,2].  Returns (cls [3,B,Q,10], reg [3,B,Q,10])."""
+        M, C = x0.shape
+        Q = M // B
+        R = tokens.shape[1]
+        dev = x0.device
+        ctx = dict(B=B, Q=Q, R=R, C=C, enc=[], layers=[])
+        # ---- radar encoders (H:531-536)
+        t2 = tokens.reshape(B * R, NUM_RADAR_FEATS)
+        enc = ctx["enc"]
+        xyz = t2[:, :3]
+        pe = self._ln(enc, self._linear(enc, xyz, "radar_position_encoder.0.weight", "radar_position_encoder.0.bias"),
+                      "radar_position_encoder.1", relu=True)
+        pos = self._ln(enc, self._linear(enc, pe, "radar_position_encoder.3.weight", "radar_position_encoder.3.bias"),
+                       "radar_position_encoder.4", relu=True)
+        n_pos = len(enc)
+        f = self._linear(enc, t2, "radar_feat_encoder.0.weight", "radar_feat_encoder.0.bias", relu=True)
+        f = self._linear(enc, f, "radar_feat_encoder.2.weight", "radar_feat_encoder.2.bias", relu=True)
+        self._linear(enc, f, "radar_feat_encoder.4.weight", "radar_feat_encoder.4.bias", relu=True)   # taped: ReLU mask
+        # kvfeat = pos + relu(feat) (H:536): the same small GEMM once more with the sum fused as its post-add epilogue
+        kvfeat_sum, _ = ops.linear(f, self.p["radar_feat_encoder.4.weight"], self.p["radar_feat_encoder.4.bias"], relu=True,
+                                   post_add=pos)
+        ctx["n_pos"] = n_pos
+        ctx["kvfeat"] = kvfeat_sum
+        cls_all = torch.empty((3, B, Q, 10), device=dev, dtype=torch.float32)
+        reg_all = torch.empty((3, B, Q, 10), device=dev, dtype=torch.float32)
+        x, anchor, centre_norm = x0, ref, True
+        for li in range(3):
+            s, m = _SUF[li], _NUM[li]
+            tape = []
+            mha = "rf_multihead_attn" + m
+            lo, hi = RADIUS_CLAMP[li]
+            geom = ops.radar_geometry(anchor, code, self.pc_range, lo, hi, centre_is_normalised=centre_norm)
+            q = self._linear(tape, x, mha + ".in_proj_weight", mha + ".in_proj_bias", w_rows=(0, C))
+            kv = self._linear(tape, kvfeat_sum, mha + ".in_proj_weight", mha + ".in_proj_bias", w_rows=(C, 3 * C))
+            kv3 = kv.view(B, R, 2 * C)
+            att, row_any = ops.attention(q.view(B, Q, C), kv3[:, :, :C], kv3[:, :, C:], self.heads, geom=geom, key_xy=key_xy,
+                                         want_row_any=True, algo="sparse")
+            gate = row_any.view(M)
+            z2 = self._linear(tape, att.view(M, C), mha + ".out_proj.weight", mha + ".out_proj.bias", residual=x, gate=gate)
+            x2 = self._ln(tape, z2, "rf_norm2" + s)
+            h = self._linear(tape, x2, "rf_linear1" + s + ".weight", "rf_linear1" + s + ".bias", relu=True)
+            z3 = self._linear(tape, h, "rf_linear2" + s + ".weight", "rf_linear2" + s + ".bias", residual=x2)
+            x3 = self._ln(tape, z3, "rf_norm3" + s)
+            n_trunk = len(tape)
+            c = self._ln(tape, self._linear(tape, x3, f"final_cls{m}.0.weight", f"final_cls{m}.0.bias"), f"final_cls{m}.1", relu=True)
+            c = self._ln(tape, self._linear(tape, c, f"final_cls{m}.3.weight", f"final_cls{m}.3.bias"), f"final_cls{m}.4", relu=True)
+            cls = self._linear(tape, c, f"final_cls{m}.6.weight", f"final_cls{m}.6.bias")
+            n_cls = len(tape)
+            g = self._linear(tape, x3, f"final_reg{m}.0.weight", f"final_reg{m}.0.bias", relu=True)
+            g = self._linear(tape, g, f"final_reg{m}.2.weight", f"final_reg{m}.2.bias", relu=True)
+            reg = self._linear(tape, g, f"final_reg{m}.4.weight", f"final_reg{m}.4.bias")
+            if li == 0:   # H:596-600: x,y of the refined reference in metres, z left normalised (quirk Q3)
+                ops.box_anchor_add(reg, anchor, 0, 2, True, self.pc_range)
+            else:         # H:664-665, H:722-723
+                ops.box_anchor_add(reg, anchor, 0, 4, False, self.pc_range)
+            cls_all[li].view(M, 10).copy_(cls)
+            reg_all[li].view(M, 10).copy_(reg)
+            ctx["layers"].append(dict(tape=tape, n_trunk=n_trunk, n_cls=n_cls, q=q, kv=kv, geom=geom, gate=gate))
+            x, anchor, code, centre_norm = x3, reg, reg, False
+        ctx["key_xy"] = key_xy
+        self.ctx = ctx
+        return cls_all, reg_all
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, d_cls, d_reg):
+        """d_cls / d_reg: [3,B,Q,10] upstream gradients.  Accumulates into ``self.flat_grad`` (zero it per step)."""
+        ctx = self.ctx
+        B, Q, R, C = ctx["B"], ctx["Q"], ctx["R"], ctx["C"]
+        M = B * Q
+        dev = d_cls.device
+        d_kvfeat = None                     # running gradient of the radar key/value features [B*R, C]
+        dx_next = None                      # gradient flowing into this layer's output x3 from the next layer
+        d_reg_next = None                   # gradient of the next layer's regression (anchor path)
+        for li in (2, 1, 0):
+            L = ctx["layers"][li]
+            tape, n_trunk, n_cls = L["tape"], L["n_trunk"], L["n_cls"]
+            dreg = d_reg[li].reshape(M, 10).contiguous().clone()
+            if d_reg_next is not None:      # reg_{l+1}[:, (0,1,4)] += reg_l[:, (0,1,4)]  ->  dreg_l[:, (0,1,4)] += dreg_{l+1}
+                ops.box_anchor_add(dreg, d_reg_next, 0, 4, False, self.pc_range)
+            d_reg_next = dreg
+            # regression head (3 linears), classification head (linear, LN, linear, LN, linear): both end in dx3
+            dg = self._linear_bwd(tape[n_cls + 2], dreg)
+            dg = self._linear_bwd(tape[n_cls + 1], dg)
+            dx3 = self._linear_bwd(tape[n_cls + 0], dg, dx_accum=dx_next)
+            dc = self._linear_bwd(tape[n_trunk + 4], d_cls[li].reshape(M, 10).contiguous())
+            dc = self._ln_bwd(tape[n_trunk + 3], dc)
+            dc = self._linear_bwd(tape[n_trunk + 2], dc)
+            dc = self._ln_bwd(tape[n_trunk + 1], dc)
+            dx3 = self._linear_bwd(tape[n_trunk + 0], dc, dx_accum=dx3)
+            # trunk, reversed: ln3, linear2(+res x2), linear1(relu), ln2, out_proj(+res x, gate), attention, kv, q
+            dz3 = self._ln_bwd(tape[6], dx3)
+            dh = self._linear_bwd(tape[5], dz3)
+            dx2 = self._linear_bwd(tape[4], dh, dx_accum=dz3)               # + skip connection z3 = x2 + ...
+            dz2 = self._ln_bwd(tape[3], dx2)
+            datt = self._linear_bwd(tape[2], dz2)                            # gate applied inside
+            kv3 = L["kv"].view(B, R, 2 * C)
+            dkv = torch.zeros((B, R, 2 * C), device=dev, dtype=torch.float32)
+            dq = ops.attention_sparse_bwd(L["q"].view(B, Q, C), kv3[:, :, :C], kv3[:, :, C:], datt.view(B, Q, C), self.heads,
+                                          L["geom"], ctx["key_xy"], dkv[:, :, :C], dkv[:, :, C:])
+            d_kvfeat = self._linear_bwd(tape[1], dkv.view(B * R, 2 * C), dx_accum=d_kvfeat)
+            dx_next = self._linear_bwd(tape[0], dq.view(M, C), dx_accum=dz2, need_dx=li > 0)   # + skip z2 = x + ...
+        # ---- radar encoders: kvfeat = pos + relu(feat)
+        enc, n_pos = ctx["enc"], ctx["n_pos"]
+        df = self._linear_bwd(enc[n_pos + 2], d_kvfeat)
+        df = self._linear_bwd(enc[n_pos + 1], df)
+        self._linear_bwd(enc[n_pos + 0], df, need_dx=False)
+        dp = self._ln_bwd(enc[3], d_kvfeat)
+        dp = self._linear_bwd(enc[2], dp)
+        dp = self._ln_bwd(enc[1], dp)
+        self._linear_bwd(enc[0], dp, need_dx=False)
+        self.ctx = None
+        return self.g
+
+
+class _RadarHeadFunction(torch.autograd.Function):
+    """Autograd bridge: forward / backward are the library-kernel passes above; the parameters enter as inputs so that
+    ``loss.backward()`` deposits their gradients like for any other module."""
+
+    @staticmethod
+    def forward(ctx, trainer, x0, ref, code, tokens, key_xy, B, *params):
+        ctx.trainer = trainer
+        ctx.n = len(params)
+        with torch.no_grad():
+            cls_all, reg_all = trainer.forward(x0, ref, code, tokens, key_xy, B)
+        return cls_all, reg_all
+
+    @staticmethod
+    def backward(ctx, d_cls, d_reg):
+        tr = ctx.trainer
+        with torch.no_grad():
+            tr.flat_grad.zero_()
+            grads = tr.backward(d_cls.contiguous(), d_reg.contiguous())
+        return (None,) * 7 + tuple(grads[k].clone() for k in tr.names)
+
+
+def radar_head_apply(trainer, named_params, x0, ref, code, tokens, key_xy, B):
+    """``named_params``: dict name -> nn.Parameter (live); order follows ``trainer.names``."""
+    plist = [named_params[k] for k in trainer.names]
+    return _RadarHeadFunction.apply(trainer, x0, ref, code, tokens, key_xy, B, *plist)
