@@ -34,7 +34,7 @@ extern "C" {
 #define TC_API
 #endif
 
-#define TC_ABI_VERSION 3
+#define TC_ABI_VERSION 4
 #define TC_MAX_LEVELS 4
 #define TC_MAX_CAMS 8
 
@@ -130,6 +130,75 @@ typedef struct {
   void*  out_bf16; int64_t ld_out_bf16;
 } tc_linear_args;
 TC_API int tc_linear(const tc_linear_args* a, tc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3c  row-local Linear CHAIN: up to TC_CHAIN_MAX_STAGES dependent Linear layers evaluated for one 128-row tile per
+ * CTA with every intermediate activation kept on chip (bf16 A operands in shared memory, fp32 accumulators and
+ * residual stream in tensor memory).  Replaces, in one launch each, the row-local tails of the path:
+ *   decoder layer  T:375-378 + mmcv FFN / norms (cfg :65-82) + T:190-203:
+ *        output_proj + pos_feat + residual + LN -> FFN (256-512-256) + LN -> reg_branches[l] (3 Linear) -> ref update
+ *   post-attention T:362 / mmcv MultiheadAttention out_proj: out_proj + residual + LN -> attention_weights (24 logits)
+ *   radar layer    H:578-611 (and :642-668, :700-729): out_proj (row gate, quirk Q6) + LN -> FFN + LN ->
+ *        final_reg* (3 Linear) + anchor add; final_cls* (Linear LN ReLU x2 -> Linear) as a second chain.
+ * The chain is a small program: stage s computes  acc[s] (+)= act[a_buf] * W_s^T  (tcgen05, K <= 256, N <= 256) and an
+ * epilogue routes the result: to a shared-memory activation buffer (the next stage's A operand), back to tensor memory
+ * as a later stage's pre-loaded accumulator (residual), and / or to global memory.
+ *
+ *   stage.W        bf16 [N, K] row-major (row stride ldw elements); a sub-block of a larger weight is a stage of its own
+ *                  (FFN hidden dim 512 = two (W1 half, W2 half) stage pairs accumulating into the same columns)
+ *   stage.a_buf    activation buffer (0 / 1) read as A; stage 0 reads the global A [M, K] (TMA) through buffer a_buf
+ *   stage.acc_col  tensor-memory column of the fp32 accumulator (multiple of 32, acc_col + N <= 512)
+ *   stage.accumulate  != 0: the product is added to what the columns already hold (pre-load or earlier partial sum)
+ *   stage.init     != 0: before the MMAs the accumulator is pre-loaded with
+ *                  (row_gate[m] ? init_bias[n] : 0) + residual[m, n] + residual2[m, n]        (NULL terms skipped)
+ *   stage.epi      TC_CHAIN_NONE  nothing (partial sum stays in tensor memory)
+ *                  TC_CHAIN_ACT   y = acc + bias, optional ReLU
+ *                  TC_CHAIN_LN    y = LayerNorm_N(acc + bias) * gamma + beta, optional ReLU
+ *                  TC_CHAIN_OUT   N <= 32: y = acc + bias + row_bias[m % period]; optional tail (below)
+ *   outputs of y   dst_buf >= 0: bf16 to activation buffer dst_buf;  keep_col >= 0: fp32 (+ fold_bias[n]) to tensor
+ *                  memory columns keep_col.. (the accumulator pre-load of a later residual stage);
+ *                  out_f32 / out_bf16: global [M, N]; out_f32_add[m, n] (optional) is added to the out_f32 copy only
+ *                  (the next kernel's residual = this output + the position feature, T:377-378)
+ *   stage.tail     TC_CHAIN_TAIL_REF_UPDATE (T:195-203): tail_out[m, 0:3] = sigmoid(y[{0,1,4}] + logit(tail_in[m, 0:3]))
+ *                  TC_CHAIN_TAIL_ANCHOR_ADD (H:596-600, :664-665, :722-723): y[0:2] += anchor xy, y[4] += anchor z before
+ *                  the store; anchor = tail_in[m, {tail_xy_col, tail_xy_col + 1, tail_z_col}], xy mapped from [0,1] to
+ *                  metres with pc_range when tail_from_norm != 0 (z added as is: quirk Q3)
+ * All fp32 row operands must be 32-byte aligned with row strides that are multiples of 8 elements.
+ */
+#define TC_CHAIN_MAX_STAGES 12
+enum { TC_CHAIN_NONE = 0, TC_CHAIN_ACT = 1, TC_CHAIN_LN = 2, TC_CHAIN_OUT = 3 };
+enum { TC_CHAIN_TAIL_NONE = 0, TC_CHAIN_TAIL_REF_UPDATE = 1, TC_CHAIN_TAIL_ANCHOR_ADD = 2 };
+typedef struct {
+  const void* W; int64_t ldw;
+  int32_t K, N;
+  int32_t a_buf, acc_col, accumulate;
+  int32_t epi, relu;
+  int32_t dst_buf, keep_col;
+  int32_t init;
+  const float* init_bias;
+  const float* residual;  int64_t ld_residual;
+  const float* residual2; int64_t ld_residual2;
+  const uint8_t* row_gate;
+  const float* bias;
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
+  const float* fold_bias;
+  const float* row_bias; int32_t row_bias_period; int64_t ld_row_bias;
+  float* out_f32;  int64_t ld_out_f32;
+  const float* out_f32_add; int64_t ld_out_f32_add;
+  void*  out_bf16; int64_t ld_out_bf16;
+  int32_t tail;
+  const float* tail_in; int64_t ld_tail_in;
+  float* tail_out;
+  int32_t tail_xy_col, tail_z_col, tail_from_norm;
+  float pc_range[6];
+} tc_chain_stage;
+typedef struct {
+  const void* A; int64_t lda;       /* bf16 [M, K] */
+  int32_t M, K;
+  int32_t num_stages;
+  tc_chain_stage stage[TC_CHAIN_MAX_STAGES];
+} tc_chain_args;
+TC_API int tc_linear_chain(const tc_chain_args* a, tc_stream_t stream);
 
 /* Fused 3 -> C position encoder head: Y = ReLU(LayerNorm(Linear_{3->C}(f(x)))), f = inverse_sigmoid (eps 1e-5,
  * T:17-32) when logit_input != 0 else identity.  Replaces T:377 (position_encoder[0:3]) and H:533

@@ -455,6 +455,11 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 }  // namespace
 
+// shared with chain_tc.cu: cached K-major SWIZZLE_128B tensor map, box = [64 cols, box_rows rows]
+bool tensor_map_bf16_2d(const void* ptr, long long ld, int rows, int cols, int box_rows, CUtensorMap* out) {
+  return get_map(ptr, ld, rows, cols, box_rows, out);
+}
+
 // 256-bit row accesses: every row-wise operand 32-byte aligned, pitch a multiple of 32 bytes
 static bool epilogue_vectorizable(const tc_linear_args* a) {
   if (a->row_bias && (!al32(a->row_bias) || a->ld_row_bias % 8 != 0)) return false;

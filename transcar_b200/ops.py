@@ -181,6 +181,100 @@ def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, 
     return out_f32, out_bf16
 
 
+_CHAIN_EPI = {"none": _lib.TC_CHAIN_NONE, "act": _lib.TC_CHAIN_ACT, "ln": _lib.TC_CHAIN_LN, "out": _lib.TC_CHAIN_OUT}
+
+
+def chain_stage(W, *, a_buf=0, acc_col=0, accumulate=False, epi="act", relu=False, dst_buf=-1, keep_col=-1,
+                init_bias=None, residual=None, residual2=None, row_gate=None, bias=None, ln=None, ln_eps=1e-5,
+                fold_bias=None, row_bias=None, row_bias_period=0, out_f32=None, out_f32_add=None,
+                out_bf16=None, ref_update=None, anchor_add=None):
+    """One stage of ``linear_chain`` (see ``tc_linear_chain`` in include/transcar_b200.h).  ``W`` is a bf16 [N,K] view.
+    ``ref_update=(ref_in [M,3], ref_out [M,3])``; ``anchor_add=(anchor [M,ld], xy_col, z_col, from_norm, pc_range)``."""
+    return dict(W=W, a_buf=a_buf, acc_col=acc_col, accumulate=accumulate, epi=epi, relu=relu, dst_buf=dst_buf,
+                keep_col=keep_col, init_bias=init_bias, residual=residual, residual2=residual2, row_gate=row_gate,
+                bias=bias, ln=ln, ln_eps=ln_eps, fold_bias=fold_bias, row_bias=row_bias,
+                row_bias_period=row_bias_period, out_f32=out_f32, out_f32_add=out_f32_add, out_bf16=out_bf16,
+                ref_update=ref_update,
+                anchor_add=anchor_add)
+
+
+def linear_chain(A, stages, label="chain"):
+    """Row-local chain of Linear layers in one launch: A [M,K] bf16, ``stages`` = list of ``chain_stage(...)`` dicts.
+    Outputs are the tensors named by the stages (``out_f32`` / ``out_bf16`` / ``ref_update[1]``)."""
+    lib = _lib.load()
+    A, lda = _rows(_need(A, "A", torch.bfloat16), "A")
+    a = _lib.ChainArgs()
+    a.A, a.lda, a.M, a.K, a.num_stages = A.data_ptr(), lda, A.shape[0], A.shape[1], len(stages)
+    if len(stages) > _lib.TC_CHAIN_MAX_STAGES:
+        raise RuntimeError(f"transcar_b200.linear_chain: at most {_lib.TC_CHAIN_MAX_STAGES} stages")
+    keep = [A]
+    M = A.shape[0]
+
+    def f32rows(t, name):
+        t2, ld = _rows(_need(t, name, torch.float32), name)
+        assert t2.shape[0] == M, (name, t2.shape, M)
+        keep.append(t2)
+        return t2.data_ptr(), ld
+
+    def f32vec(t, name):
+        _need(t, name, torch.float32)
+        keep.append(t)
+        return t.data_ptr()
+
+    for i, sd in enumerate(stages):
+        st = a.stage[i]
+        W, ldw = _rows(_need(sd["W"], "W", torch.bfloat16), "W")
+        keep.append(W)
+        st.W, st.ldw, st.N, st.K = W.data_ptr(), ldw, W.shape[0], W.shape[1]
+        st.a_buf, st.acc_col, st.accumulate = sd["a_buf"], sd["acc_col"], 1 if sd["accumulate"] else 0
+        st.epi, st.relu = _CHAIN_EPI[sd["epi"]], 1 if sd["relu"] else 0
+        st.dst_buf, st.keep_col = sd["dst_buf"], sd["keep_col"]
+        st.init = 1 if (sd["init_bias"] is not None or sd["residual"] is not None or sd["residual2"] is not None) else 0
+        if sd["init_bias"] is not None:
+            st.init_bias = f32vec(sd["init_bias"], "init_bias")
+        if sd["residual"] is not None:
+            st.residual, st.ld_residual = f32rows(sd["residual"], "residual")
+        if sd["residual2"] is not None:
+            st.residual2, st.ld_residual2 = f32rows(sd["residual2"], "residual2")
+        if sd["row_gate"] is not None:
+            st.row_gate = _need(sd["row_gate"], "row_gate", torch.uint8).data_ptr()
+        if sd["bias"] is not None:
+            st.bias = f32vec(sd["bias"], "bias")
+        if sd["ln"] is not None:
+            st.ln_gamma, st.ln_beta = f32vec(sd["ln"][0], "ln_gamma"), f32vec(sd["ln"][1], "ln_beta")
+        st.ln_eps = float(sd["ln_eps"])
+        if sd["fold_bias"] is not None:
+            st.fold_bias = f32vec(sd["fold_bias"], "fold_bias")
+        if sd["row_bias"] is not None:
+            rb, ldrb = _rows(_need(sd["row_bias"], "row_bias", torch.float32), "row_bias")
+            keep.append(rb)
+            st.row_bias, st.ld_row_bias, st.row_bias_period = rb.data_ptr(), ldrb, sd["row_bias_period"] or rb.shape[0]
+        if sd["out_f32"] is not None:
+            st.out_f32, st.ld_out_f32 = f32rows(sd["out_f32"], "out_f32")
+        if sd["out_f32_add"] is not None:
+            st.out_f32_add, st.ld_out_f32_add = f32rows(sd["out_f32_add"], "out_f32_add")
+        if sd["out_bf16"] is not None:
+            o, ldo = _rows(_need(sd["out_bf16"], "out_bf16", torch.bfloat16), "out_bf16")
+            keep.append(o)
+            st.out_bf16, st.ld_out_bf16 = o.data_ptr(), ldo
+        if sd["ref_update"] is not None:
+            rin, rout = sd["ref_update"]
+            st.tail = _lib.TC_CHAIN_TAIL_REF_UPDATE
+            st.tail_in, st.ld_tail_in = f32rows(rin, "ref_in")
+            if not rout.is_contiguous() or rout.shape[-1] != 3:
+                raise RuntimeError("transcar_b200.linear_chain: ref_out must be contiguous [M,3]")
+            st.tail_out = _need(rout, "ref_out", torch.float32).data_ptr()
+        elif sd["anchor_add"] is not None:
+            anchor, xy_col, z_col, from_norm, pc_range = sd["anchor_add"]
+            st.tail = _lib.TC_CHAIN_TAIL_ANCHOR_ADD
+            st.tail_in, st.ld_tail_in = f32rows(anchor, "anchor")
+            st.tail_xy_col, st.tail_z_col, st.tail_from_norm = xy_col, z_col, 1 if from_norm else 0
+            for j in range(6):
+                st.pc_range[j] = float(pc_range[j])
+    lbl = label if TIMELINE is None else f"{label} M{M} x{len(stages)}"
+    _lib.check(_call(lbl, lib.tc_linear_chain, C.byref(a), _stream()), "linear_chain")
+
+
 def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, want_f32=True, want_bf16=False):
     """ReLU(LN(Linear_{3->C}(f(x[:, :3])))); x [M, ldx>=3] fp32."""
     lib = _lib.load()
