@@ -8,8 +8,9 @@
 // roofline.  Here the texels are staged through shared memory with cp.async (LDGSTS: no registers held while in
 // flight) and the issue of a pair is decoupled from its consumption by a per-warp ring:
 //
-//   * one warp per (sample, query), persistent warps striding over the queries; the next query's reference
-//     point / logits / camera matrices are prefetched into registers one query ahead;
+//   * one warp per (sample, query), persistent warps: a CTA owns a contiguous range of queries and hands them to its
+//     warps through a shared-memory counter (valid cameras per query vary 0..3, a static assignment leaves a tail);
+//     the next query's reference point / logits / camera matrices are prefetched into registers one query ahead;
 //   * lane c < N projects the query through camera c's lidar2img (fp32, reference op order, bit-exact mask),
 //     a ballot yields the valid-camera set (~18 % of the pairs are valid);
 //   * for every valid pair and every 512-byte channel chunk, lanes 0..15 each own ONE texel (level = lane/4,
@@ -22,22 +23,23 @@
 //     ring is full, and stores a query's channels once its last camera has been consumed.
 // (A cp.async.bulk per texel was measured first: UBLKCP takes uniform registers, so 16 per-lane copies turn into a
 // serialised ELECT/R2UR loop that cost a third of the kernel.)
-// 12 warps x 2 slots x 8 KB = 192 KB of shared memory per CTA, one CTA per SM.
+// 24 warps x 1 slot (bf16 in/out, 80 registers) or 12 warps x 2 slots (fp32 variants) x 8 KB = 192 KB of shared memory
+// per CTA, one CTA per SM.  Measured and rejected (round 1): a global atomic query counter (7200 same-address atomics
+// cost more than the tail they remove) and the 16-texel weighted sum as mma.sync m16n8k16 with 3-way bf16-split weights
+// (bit-accurate, but the accumulator fragment leaves 1 lane in 4 with useful data: the per-query epilogue cost more
+// than the 192 FMA/unpack instructions it replaced; 13-17 us vs 10.5 us).
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace tc {
 namespace {
 
-constexpr int kWarps = 12;
-constexpr int kSlots = 2;
 constexpr int kTexels = 16;                     // 4 levels x 4 corners
 constexpr int kChunkBytes = 512;                // bytes of one texel handled per pass: 256 bf16 or 128 fp32 channels
 constexpr int kSlotBytes = kTexels * kChunkBytes;
-constexpr int kRingBytes = kWarps * kSlots * kSlotBytes;             // 196608
-constexpr int kWeightBytes = kWarps * kSlots * kTexels * 4;          // bilinear * sigmoid weight per texel
-constexpr int kIndexBytes = kWarps * kSlots * kTexels * 4;           // texel index per texel
-constexpr int kMetaBytes = kWarps * kSlots * 16;                     // row, channel offset, flags, pad
-constexpr int kSampleSmem = kRingBytes + kWeightBytes + kIndexBytes + kMetaBytes;
+// shared memory of a CTA with `warps` warps of `slots` ring slots each: ring + per-slot weights, texel indices, meta
+constexpr int sample_smem(int warps, int slots) { return warps * slots * (kSlotBytes + kTexels * 4 + kTexels * 4 + 16) + 16; }
 
 struct SampleParams {
   const void* feat[TC_MAX_LEVELS];
@@ -49,6 +51,7 @@ struct SampleParams {
   const float* logits;
   float pc[6];
   float inv_w, inv_h;      // 1.0f / img_w, 1.0f / img_h
+  float inv_q;             // 1.0f / Q
   void* out;
   uint8_t* mask;
 };
@@ -72,6 +75,14 @@ __device__ __forceinline__ void cp_async_wait(unsigned n) {
   }
 }
 
+// query row of task t: floor(t / Q) without an integer division (t, Q < 2^30; inv_q = 1.0f / Q)
+__device__ __forceinline__ int row_of(int t, int Q, float inv_q) {
+  int b = (int)((float)t * inv_q);
+  b += ((b + 1) * Q <= t) ? 1 : 0;
+  b -= (b * Q > t) ? 1 : 0;
+  return b;
+}
+
 // Per-query inputs, fetched one query ahead of their use.
 struct QueryIn {
   float rx, ry, rz, logit;
@@ -79,7 +90,7 @@ struct QueryIn {
 };
 
 __device__ __forceinline__ void fetch_query(const SampleParams& p, int task, int lane, QueryIn& in) {
-  const int b = task / p.Q;
+  const int b = row_of(task, p.Q, p.inv_q);
   const float* r = p.ref + (size_t)task * 3;
   in.rx = __ldg(r); in.ry = __ldg(r + 1); in.rz = __ldg(r + 2);            // same address in every lane: broadcast
   in.logit = (lane < p.N * 4) ? __ldg(p.logits + (size_t)task * (p.N * 4) + lane) : 0.f;
@@ -89,20 +100,23 @@ __device__ __forceinline__ void fetch_query(const SampleParams& p, int task, int
   }
 }
 
-template <bool kBf16In, bool kBf16Out>
+template <bool kBf16In, bool kBf16Out, int kWarps, int kSlots>
 __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SampleParams p) {
   constexpr int kPer = kBf16In ? 8 : 4;                 // channels per lane per chunk (16 bytes)
   constexpr int kChunkCh = kBf16In ? 256 : 128;         // channels per 512-byte chunk
+  constexpr int kRingBytes = kWarps * kSlots * kSlotBytes;
+  constexpr int kWeightBytes = kWarps * kSlots * kTexels * 4;          // bilinear * sigmoid weight per texel
+  constexpr int kIndexBytes = kWarps * kSlots * kTexels * 4;           // texel index per texel
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* ring = smem + warp * kSlots * kSlotBytes + lane * 16;          // this lane's 16-byte column of the ring
   float* wts = reinterpret_cast<float*>(smem + kRingBytes) + warp * kSlots * kTexels;
   unsigned* tidx = reinterpret_cast<unsigned*>(smem + kRingBytes + kWeightBytes) + warp * kSlots * kTexels;
   int* meta = reinterpret_cast<int*>(smem + kRingBytes + kWeightBytes + kIndexBytes) + warp * kSlots * 4;
+  unsigned* next_ctr = reinterpret_cast<unsigned*>(smem + kRingBytes + kWeightBytes + kIndexBytes + kWarps * kSlots * 16);
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
 
   const int total = p.B * p.Q;
-  const int stride = gridDim.x * kWarps;
   const int esz = kBf16In ? 2 : 4;
   const int chunks = p.C / kChunkCh;
   unsigned issued = 0, consumed = 0;                    // ring counters (warp-uniform)
@@ -163,15 +177,30 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SamplePara
     __syncwarp();                      // every lane has read the slot's weights / meta before they are overwritten
   };
 
-  int task = blockIdx.x * kWarps + warp;
+  // Work distribution: a CTA owns a contiguous range of queries; its warps take the first kWarps statically and the
+  // rest from a shared-memory counter (the number of valid cameras per query varies 0..3, so a static assignment
+  // leaves some warps with twice the average work).  A warp knows its next query one iteration ahead (`next`), so
+  // that query's inputs are prefetched.
+  const int range_begin = (int)(((long long)total * blockIdx.x) / gridDim.x);
+  const int range_end = (int)(((long long)total * (blockIdx.x + 1)) / gridDim.x);
+  if (threadIdx.x == 0) *next_ctr = kWarps;
+  __syncthreads();
+  auto grab = [&]() -> int {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(next_ctr, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    return min(range_end, range_begin + (int)t);
+  };
+  int task = min(range_end, range_begin + warp);
   QueryIn cur, nxt;
   pdl_trigger();
   pdl_wait();            // reference points and logits come from the previous kernels
-  if (task < total) fetch_query(p, task, lane, cur);
+  if (task < range_end) fetch_query(p, task, lane, cur);
   nxt = cur;
+  int next = task < range_end ? grab() : range_end;
 
-  for (; task < total; task += stride, cur = nxt) {
-    const int b = task / p.Q;
+  for (; task < range_end; task = next, next = (next < range_end ? grab() : range_end), cur = nxt) {
+    const int b = row_of(task, p.Q, p.inv_q);
 
     // -- projection: lane c handles camera c (T:389-409), fp32, reference op order ------------------
     const float px = __fadd_rn(__fmul_rn(cur.rx, p.pc[3] - p.pc[0]), p.pc[0]);
@@ -205,7 +234,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SamplePara
     const float wgt = (lane < p.N * 4) ? sigmoid_f32(cur.logit) : 0.f;
 
     // -- next query's inputs: issued now, consumed in the next iteration ------------------------------
-    if (task + stride < total) fetch_query(p, task + stride, lane, nxt);
+    if (next < range_end) fetch_query(p, next, lane, nxt);
 
     if (vset == 0) {                                    // no camera sees the point: the masked sum is exactly 0
       for (int c = lane * kPer; c < p.C; c += 32 * kPer) {
@@ -302,6 +331,30 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
+template <bool kBf16In, bool kBf16Out, int kWarps, int kSlots>
+cudaError_t launch_sample(const SampleParams& p, long long total, int sm_count, cudaStream_t s) {
+  constexpr int smem = sample_smem(kWarps, kSlots);
+  static bool configured = false;
+  auto kernel = sample_kernel<kBf16In, kBf16Out, kWarps, kSlots>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const long long ctas = (total + kWarps - 1) / kWarps;
+  return launch(kernel, dim3((unsigned)(ctas < sm_count ? ctas : sm_count)), dim3(kWarps * 32), (size_t)smem, s, 1u, p);
+}
+
+// Tuning hook (tools/k1_bench.py): TC_SAMPLE_VARIANT picks the warps x ring-slots shape of the bf16 kernel.
+int sample_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TC_SAMPLE_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 }  // namespace
 }  // namespace tc
 
@@ -330,33 +383,29 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   p.B = a->B; p.N = a->N; p.Q = a->Q; p.C = a->C;
   p.ref = a->ref; p.lidar2img = a->lidar2img; p.logits = a->attn_logits;
   for (int i = 0; i < 6; ++i) p.pc[i] = a->pc_range[i];
-  p.inv_w = 1.0f / a->img_w; p.inv_h = 1.0f / a->img_h;
+  p.inv_w = 1.0f / a->img_w; p.inv_h = 1.0f / a->img_h; p.inv_q = 1.0f / (float)a->Q;
   p.out = a->out; p.mask = a->mask;
-  // persistent warps, one CTA per SM (192 KB ring); warp w handles queries w, w + W, ...
+  // persistent warps, one CTA per SM; each CTA hands its range of queries out to its warps dynamically
   static int sm_count = 0;
-  static bool configured = false;
-  if (!configured) {
+  if (sm_count == 0) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
     sm_count = n;
-    cudaError_t e = cudaFuncSetAttribute(sample_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sample_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sample_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sample_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem);
-    if (e != cudaSuccess) { set_error("tc_sample_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = true;
   }
-  const long long total = (long long)a->B * a->Q;
-  const long long ctas = (total + kWarps - 1) / kWarps;
-  dim3 grid((unsigned)(ctas < sm_count ? ctas : sm_count));
-  dim3 block(kWarps * 32);
   cudaStream_t s = as_stream(stream);
   const bool bi = a->feat_dtype == TC_BF16, bo = a->out_dtype == TC_BF16;
-  if (bi && bo) launch(sample_kernel<true, true>, grid, block, kSampleSmem, s, 1u, p);
-  else if (bi) launch(sample_kernel<true, false>, grid, block, kSampleSmem, s, 1u, p);
-  else if (bo) launch(sample_kernel<false, true>, grid, block, kSampleSmem, s, 1u, p);
-  else launch(sample_kernel<false, false>, grid, block, kSampleSmem, s, 1u, p);
+  const long long total = (long long)a->B * a->Q;
+  cudaError_t e = cudaSuccess;
+  // bf16 in / bf16 out (the engine's path): 24 warps x 1 slot measured fastest (10.5 us vs 10.9 us for 12 x 2 on the
+  // bench workload, tools/k1_bench.py); the fp32 instantiations need more registers and keep 12 x 2.
+  if (bi && bo) {
+    if (sample_variant() == 1) e = launch_sample<true, true, 12, 2>(p, total, sm_count, s);
+    else e = launch_sample<true, true, 24, 1>(p, total, sm_count, s);
+  } else if (bi) e = launch_sample<true, false, 12, 2>(p, total, sm_count, s);
+  else if (bo) e = launch_sample<false, true, 12, 2>(p, total, sm_count, s);
+  else e = launch_sample<false, false, 12, 2>(p, total, sm_count, s);
+  if (e != cudaSuccess) { set_error("tc_sample_fwd: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   count_launch();
   return check_launch("tc_sample_fwd");
 }

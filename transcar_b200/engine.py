@@ -183,17 +183,12 @@ class FusionDecoderEngine:
         x32, x16, ref = self._initial_state(B)
         hs, refs = [], []
         code = None
+        pos_feat = None
         for l in range(self.L):
             p = f"transformer.decoder.layers.{l}."
-            # --- branch: position encoder of the cross-attention (T:377) - needs the reference points only
-            with self._branch(0):
-                pe, pe16 = ops.point_embed(ref, self.f32[p + "attentions.1.position_encoder.0.weight"],
-                                           self.f32[p + "attentions.1.position_encoder.0.bias"],
-                                           *self._ln(p + "attentions.1.position_encoder.1"), logit_input=True,
-                                           want_f32=not self.bf16, want_bf16=self.bf16)
-                pos_feat = self._lin(pe16 if self.bf16 else pe, p + "attentions.1.position_encoder.3",
-                                     ln=self._ln(p + "attentions.1.position_encoder.4"), relu=True)
-                self._keep.extend((pe, pe16))
+            if l == 0:      # layers > 0: issued on the side stream behind the previous layer's refinement (below)
+                with self._branch(0):
+                    pos_feat = self._position_encoder(p, ref)
             # --- self attention (mmcv MultiheadAttention wrapper around nn.MultiheadAttention)
             qkv = self._in_proj(x16, p + "attentions.0.attn", self.row_bias_qkv[l])
             qkv3 = qkv.view(B, Q, 3 * C)
@@ -203,6 +198,7 @@ class FusionDecoderEngine:
             # --- Detr3DCrossAtten (T:302-378)
             aw = self._lin(x16, p + "attentions.1.attention_weights", bias=False,
                            row_bias=self.row_bias_aw[l], row_bias_period=Q)
+            self._join(0, pos_feat, ref)     # reference points refined by the previous layer + their position feature
             ev = self.sample_events
             if ev is not None:          # bench.py: per-launch CUDA-event timing of K1 on the launching stream
                 e0 = torch.cuda.Event(enable_timing=True, external=self.external_events)
@@ -217,21 +213,37 @@ class FusionDecoderEngine:
                 self.cam_masks.append(cam_mask)
             if l == max(self.L - 2, 0):
                 self._start_radar_branch()
-            self._join(0, pos_feat)
             x32, x16 = self._lin(s.view(M, C), p + "attentions.1.output_proj", both=True,
                                  residual=x32, residual2=pos_feat, ln=self._ln(p + "norms.1"))
             # --- FFN (mmcv FFN: x + W2 relu(W1 x)) + norm
             h = self._lin(x16, p + "ffns.0.layers.0.0", feed=True, relu=True)
             x32, x16 = self._lin(h, p + "ffns.0.layers.1", both=True, residual=x32, ln=self._ln(p + "norms.2"))
-            # --- iterative refinement (T:190-203)
-            r = self._lin(x16, f"reg_branches.{l}.0", feed=True, relu=True)
-            r = self._lin(r, f"reg_branches.{l}.2", feed=True, relu=True)
-            code = self._lin(r, f"reg_branches.{l}.4")
-            ref = ops.ref_update(code, ref)
+            # --- branch: iterative refinement (T:190-203) and the next layer's position encoder (T:377).  The next
+            # layer's self-attention needs only x, so this chain (~45 us) hides behind in_proj + attention + out_proj.
+            with self._branch(0):
+                r = self._lin(x16, f"reg_branches.{l}.0", feed=True, relu=True)
+                r2 = self._lin(r, f"reg_branches.{l}.2", feed=True, relu=True)
+                code = self._lin(r2, f"reg_branches.{l}.4")
+                ref = ops.ref_update(code, ref)
+                self._keep.extend((x16, r, r2, code, ref))
+                if l + 1 < self.L:
+                    pos_feat = self._position_encoder(f"transformer.decoder.layers.{l + 1}.", ref)
             if keep_all or l == self.L - 1:
                 hs.append(x32)
                 refs.append(ref)
+        self._join(0, ref, code)
         return hs, refs, x32, x16, ref, code
+
+    def _position_encoder(self, p, ref):
+        """Cross-attention position encoder (T:283-292, 377): MLP on logit(ref); needs the reference points only."""
+        pe, pe16 = ops.point_embed(ref, self.f32[p + "attentions.1.position_encoder.0.weight"],
+                                   self.f32[p + "attentions.1.position_encoder.0.bias"],
+                                   *self._ln(p + "attentions.1.position_encoder.1"), logit_input=True,
+                                   want_f32=not self.bf16, want_bf16=self.bf16)
+        pos_feat = self._lin(pe16 if self.bf16 else pe, p + "attentions.1.position_encoder.3",
+                             ln=self._ln(p + "attentions.1.position_encoder.4"), relu=True)
+        self._keep.extend((pe, pe16, ref))
+        return pos_feat
 
     def _initial_state(self, B):
         """Batch-expanded query / reference points (T:119-127): input independent, built once per batch size.
