@@ -1,15 +1,24 @@
 // K4 tensor-core path: softmax(scale * Q K^T + mask) V for head dim 32, bf16 operands, fp32 accumulation.
 //
-// One CTA = 128 queries of one (sample, head); keys/values stream through a 2-stage TMA ring in 128-key tiles.
-//   S  = Q K^T   tcgen05.mma 128x128x16 (x2), both operands K-major SWIZZLE_64B, accumulator in TMEM cols [0,128)
-//   P  = online softmax of S: 4 warps, one query row per thread (tcgen05.ld 32x32b), radar distance mask evaluated
-//        in-kernel from per-query circle geometry (no sqrt: d < r  <=>  d^2 < thr(r), thr precomputed exactly),
-//        bf16 P written to shared memory in the K-major SWIZZLE_128B layout the next MMA expects
-//   O += P V     tcgen05.mma 128x32x16 (x8), A = P (shared memory), B = V tile used MN-major (SWIZZLE_64B) straight
-//        from its [keys, 32] row-major TMA image; accumulator in TMEM cols [128,160), rescaled in place
-//        (tcgen05.ld / st) when the running row maximum moves.
+// One CTA = 128 queries of one (sample, head); keys/values stream through a 6-stage TMA ring in 32-key tiles.
+//   S  = Q K^T   tcgen05.mma 128x32x16 (x2), both operands K-major SWIZZLE_64B, accumulator double-buffered in TMEM
+//        (columns [0,32) and [32,64)): S(j+1) is ready before the softmax warps finish tile j, so they never wait for a
+//        QK^T round trip (p_full -> MMA thread wakes -> MMA -> commit -> softmax wakes, ~2000 cycles when exposed)
+//   P  = online softmax of S: 4 warps, one query row per thread (one tcgen05.ld 32x32b.x32 per tile), radar distance
+//        mask evaluated in-kernel from per-query circle geometry (no sqrt: d < r  <=>  d^2 < thr(r), thr precomputed
+//        exactly), bf16 P written to shared memory (two buffers) in the K-major SWIZZLE_64B layout the next MMA expects
+//   O += P V     tcgen05.mma 128x32x16 (x2), A = P (shared memory), B = V tile used MN-major (SWIZZLE_64B) straight
+//        from its [keys, 32] row-major TMA image; accumulator in TMEM cols [64,96), rescaled in place (tcgen05.ld / st)
+//        only when a row maximum grows by more than 2^8 (the exponentials stay below 2^8, exact after the final 1 / l).
+//        Writing P(j) only needs PV(j-2) retired, so the softmax warps never wait for the PV round trip either.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax/epilogue.
-// Two CTAs share an SM (2 x 256 TMEM columns), so one CTA's softmax overlaps the other's MMAs.
+// The kernel is bound by the exponentials (MUFU: 16 / clk / SM -> 12 us for B = 8, 900 x 900, 8 heads) provided enough
+// softmax warps are resident to hide each warp's dependent-issue latency (~6 cycles per instruction).  FOUR CTAs share an
+// SM: 128 TMEM columns, ~50 KB of shared memory and <= 80 registers each, so the grid of 512 CTAs is one wave with 4
+// softmax warps per scheduler.  History (ncu, per launch): 128-key tiles, single S, 2 CTAs / SM: 41 us (32 % issue-active,
+// 30 % of the instructions spinning on mbarriers); 64-key tiles, double-buffered S, 2 CTAs / SM: 38 us (XU 39 %: two
+// warps per scheduler cannot hide the per-instruction latency); 64-key tiles, single S, 4 CTAs / SM: 36 us (XU 47 %: the
+// warps wait for the S round trip half of the time).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -22,10 +31,11 @@
 namespace tc {
 namespace {
 
-constexpr int kBQ = 128, kBKV = 128, kD = 32;
+constexpr int kBQ = 128, kBKV = 32, kD = 32, kStages = 6;
 constexpr int kThreads = 192;
-constexpr uint32_t kTileBytes = kBKV * kD * 2;          // 8 KB: one Q / K / V tile
-constexpr uint32_t kPHalfBytes = kBQ * 64 * 2;          // 16 KB: P for 64 keys
+constexpr uint32_t kQBytes = kBQ * kD * 2;              // 8 KB
+constexpr uint32_t kKVBytes = kBKV * kD * 2;            // 2 KB: one K or V tile
+constexpr uint32_t kPBytes = kBQ * kBKV * 2;            // 8 KB: P for 32 keys, 64-byte rows (K-major SWIZZLE_64B); two buffers
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -33,7 +43,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
 struct AttnTcParams {
   int B, Lq, Lk, heads;
   float scale_log2;                 // scale * log2(e)
@@ -45,27 +54,30 @@ struct AttnTcParams {
 
 // shared-memory carve-up (offsets from a 1024-aligned base)
 constexpr uint32_t kOffQ = 0;
-constexpr uint32_t kOffK = kOffQ + kTileBytes;                  // 2 stages
-constexpr uint32_t kOffV = kOffK + 2 * kTileBytes;              // 2 stages
-constexpr uint32_t kOffP = kOffV + 2 * kTileBytes;              // 2 halves x 16 KB  (offset 40 KB, 1024-aligned)
-constexpr uint32_t kOffKey = kOffP + 2 * kPHalfBytes;           // 2 stages x 3 x 128 floats
+constexpr uint32_t kOffK = kOffQ + kQBytes;                     // kStages x 2 KB
+constexpr uint32_t kOffV = kOffK + kStages * kKVBytes;          // kStages x 2 KB
+constexpr uint32_t kOffP = kOffV + kStages * kKVBytes;          // 2 x 8 KB (offset 32 KB)
+constexpr uint32_t kOffKey = kOffP + 2 * kPBytes;                   // 2 x 3 x 32 floats
 constexpr uint32_t kOffBar = kOffKey + 2 * 3 * kBKV * 4;
-constexpr uint32_t kSmemUsed = kOffBar + 128;
-constexpr uint32_t kSmemBytes = 100 * 1024;                     // padded so that at most 2 CTAs fit on an SM
+constexpr uint32_t kSmemUsed = kOffBar + 192;
+constexpr uint32_t kSmemBytes = kSmemUsed + 1024;               // + slack for the 1024-byte alignment of the base
+constexpr uint32_t kTmemCols = 128;                             // S0 [0,32), S1 [32,64), O [64,96); 4 CTAs x 128 = all 512 columns
+static_assert(kOffP % 512 == 0 && kPBytes % 512 == 0, "SWIZZLE_64B tile alignment");
 
 template <bool kMask>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kMask ? 2 : 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  // barriers: 0 q_full, 1-2 kv_full, 3-4 kv_empty, 5 s_full, 6 p_full, 7 o_done; then the TMEM slot
+  // barriers: q_full, kv_full[kStages], kv_empty[kStages], then s_full[2], p_full[2], o_done[2] (tile j uses index j & 1,
+  // phase parity (j >> 1) & 1: nobody is ever more than one phase behind such a barrier); then the TMEM slot
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t q_full = bar0, kv_full = bar0 + 8, kv_empty = bar0 + 24, s_full = bar0 + 40, p_full = bar0 + 48,
-                 o_done = bar0 + 56;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t q_full = bar0, kv_full = bar0 + 8, kv_empty = kv_full + 8 * kStages, s_full = kv_empty + 8 * kStages,
+                 p_full = s_full + 16, o_done = p_full + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * kStages);
   float* key_geo = reinterpret_cast<float*>(smem + kOffKey);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,79 +87,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    mbar_init(kv_full, 1); mbar_init(kv_full + 8, 1);
-    mbar_init(kv_empty, 1); mbar_init(kv_empty + 8, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_done, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
+    mbar_init(s_full, 1); mbar_init(s_full + 8, 1);
+    mbar_init(p_full, 128); mbar_init(p_full + 8, 128);
+    mbar_init(o_done, 1); mbar_init(o_done + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * kBKV;
   pdl_wait();            // q / k / v / geometry come from the previous kernels
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0 && T > 0) {
-      mbar_expect_tx(q_full, kTileBytes);
+      mbar_expect_tx(q_full, kQBytes);
       tma_load_3d(sbase + kOffQ, &map_q, h * kD, q0, b, q_full);
       for (int j = 0; j < T; ++j) {
-        const int s = j & 1;
-        mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(kv_full + 8 * s, 2 * kTileBytes);
-        tma_load_3d(sbase + kOffK + s * kTileBytes, &map_k, h * kD, j * kBKV, b, kv_full + 8 * s);
-        tma_load_3d(sbase + kOffV + s * kTileBytes, &map_v, h * kD, j * kBKV, b, kv_full + 8 * s);
+        const int s = j % kStages;
+        mbar_wait(kv_empty + 8 * s, ((j / kStages) & 1) ^ 1);
+        mbar_expect_tx(kv_full + 8 * s, 2 * kKVBytes);
+        tma_load_3d(sbase + kOffK + s * kKVBytes, &map_k, h * kD, j * kBKV, b, kv_full + 8 * s);
+        tma_load_3d(sbase + kOffV + s * kKVBytes, &map_v, h * kD, j * kBKV, b, kv_full + 8 * s);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && T > 0) {
-      // kind::f16 descriptors: D=F32, A=B=BF16; S: M=128,N=128 (both K-major); O: M=128,N=32, B MN-major (bit 16)
-      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // kind::f16 descriptors: D=F32, A=B=BF16; S: M=128,N=64 (both K-major); O: M=128,N=32, B MN-major (bit 16)
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBKV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // (A and B must share one 16-bit format: an FP16 P against a BF16 V is rejected as an illegal instruction - measured.)
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t dq = make_desc_sw64_kmajor(sbase + kOffQ);
-      mbar_wait(q_full, 0);
-      mbar_wait(kv_full, 0);
-      tc_fence_after();
-      {
-        const uint64_t dk = make_desc_sw64_kmajor(sbase + kOffK);
-        umma_bf16(tmem_S, dq, dk, idesc_s, 0u);
-        umma_bf16(tmem_S, dq + 2, dk + 2, idesc_s, 1u);
-        umma_commit(s_full);
-      }
-      for (int j = 0; j < T; ++j) {
-        const int s = j & 1;
-        mbar_wait(p_full, j & 1);                 // P(j) in smem, O rescaled, S(j) consumed
+      auto issue_s = [&](int j) {                 // S(j) -> S buffer j & 1 (free: softmax(j - 2) has arrived on p_full)
+        const int s = j % kStages;
+        mbar_wait(kv_full + 8 * s, (j / kStages) & 1);
         tc_fence_after();
+        const uint64_t dk = make_desc_sw64_kmajor(sbase + kOffK + s * kKVBytes);
+        const uint32_t d = tmem_S + (uint32_t)(j & 1) * kBKV;
+        umma_bf16(d, dq, dk, idesc_s, 0u);
+        umma_bf16(d, dq + 2, dk + 2, idesc_s, 1u);
+        umma_commit(s_full + 8 * (j & 1));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (T > 1) issue_s(1);
+      for (int j = 0; j < T; ++j) {
+        const int s = j % kStages;
+        mbar_wait(p_full + 8 * (j & 1), (j >> 1) & 1);      // P(j) in smem, O rescaled, S(j) consumed
+        tc_fence_after();
+        const uint64_t dp = make_desc_sw64_kmajor(sbase + kOffP + (j & 1) * kPBytes);
         // the tail tile multiplies only the 16-key groups that hold real keys (P is not written beyond them)
         const int ksteps = (min(kBKV, p.Lk - j * kBKV) + 15) >> 4;
 #pragma unroll
         for (int k16 = 0; k16 < kBKV / 16; ++k16) {
           if (k16 < ksteps) {
-            const uint64_t dp = make_desc_sw128(sbase + kOffP + (k16 >> 2) * kPHalfBytes) + 2 * (k16 & 3);
-            const uint64_t dv = make_desc_sw64_mnmajor(sbase + kOffV + s * kTileBytes + k16 * 1024, 8192);
-            umma_bf16(tmem_O, dp, dv, idesc_o, (j | k16) ? 1u : 0u);
+            const uint64_t dv = make_desc_sw64_mnmajor(sbase + kOffV + s * kKVBytes + k16 * 1024, kKVBytes);
+            umma_bf16(tmem_O, dp + 2 * k16, dv, idesc_o, (j | k16) ? 1u : 0u);
           }
         }
         umma_commit(kv_empty + 8 * s);            // K/V stage s may be refilled
-        umma_commit(o_done);                      // O(j) accumulated, P buffer free
-        if (j + 1 < T) {
-          const int s1 = (j + 1) & 1;
-          mbar_wait(kv_full + 8 * s1, ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          const uint64_t dk = make_desc_sw64_kmajor(sbase + kOffK + s1 * kTileBytes);
-          umma_bf16(tmem_S, dq, dk, idesc_s, 0u);
-          umma_bf16(tmem_S, dq + 2, dk + 2, idesc_s, 1u);
-          umma_commit(s_full);
-        }
+        umma_commit(o_done + 8 * (j & 1));        // O(j) accumulated, P buffer j & 1 free
+        if (j + 2 < T) issue_s(j + 2);
       }
     }
   } else {
@@ -158,6 +165,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const bool row_ok = q < p.Lq;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const int tid128 = threadIdx.x - 64;
+    const bool warp_idle = q0 + quad * 32 >= p.Lq;   // whole warp past Lq (warp-uniform: tcgen05.ld/st are warp-collective)
 
     Circle cc, cf, cr;
     float thr = 0.f;
@@ -170,165 +178,129 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
     }
     float m_run = -INFINITY, l_run = 0.f;
+    // P row of this thread: 64 bytes, 16-byte chunk c stored at c ^ ((row >> 1) & 3) (SWIZZLE_64B)
+    uint8_t* prow = smem + kOffP + row * 64;
+    const int psw = (row >> 1) & 3;
+
+    // Before P(j) is written: (rarely) rescale O by this row's correction factor - PV(j-1) must have retired - and
+    // make sure PV(j-2), the last reader of P buffer j & 1, has retired (two tiles ago: never a real wait).
+    auto sync_o = [&](int j, float corr) {
+      if (j > 0 && __any_sync(0xffffffffu, corr != 1.0f)) {
+        mbar_wait(o_done + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld32(tmem_O + lane_off, o);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+        tmem_st32(tmem_O + lane_off, o);
+      }
+      if (j > 1) mbar_wait(o_done + 8 * (j & 1), ((j - 2) >> 1) & 1);
+    };
 
     for (int j = 0; j < T; ++j) {
       const int k0 = j * kBKV;
       const int nvalid = min(kBKV, p.Lk - k0);          // real keys in this tile
-      const int nchunks = (nvalid + 31) >> 5;           // 32-key chunks that hold at least one real key
       float* kx = key_geo + (j & 1) * 3 * kBKV;
       float* ky = kx + kBKV;
       float* kn = ky + kBKV;
       if (kMask) {
-        const int key = k0 + tid128;
-        float x = 0.f, y = 0.f;
-        if (key < p.Lk) {
-          x = p.key_xy[((long long)b * p.Lk + key) * 2 + 0];
-          y = p.key_xy[((long long)b * p.Lk + key) * 2 + 1];
+        if (tid128 < kBKV) {
+          const int key = k0 + tid128;
+          float x = 0.f, y = 0.f;
+          if (key < p.Lk) {
+            x = p.key_xy[((long long)b * p.Lk + key) * 2 + 0];
+            y = p.key_xy[((long long)b * p.Lk + key) * 2 + 1];
+          }
+          kx[tid128] = x; ky[tid128] = y; kn[tid128] = key_norm(x, y);
         }
-        kx[tid128] = x; ky[tid128] = y; kn[tid128] = key_norm(x, y);
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full + 8 * (j & 1), (j >> 1) & 1);
       tc_fence_after();
-      if (q0 + quad * 32 >= p.Lq) {                     // whole warp past Lq (warp-uniform: tcgen05.ld/st are warp-collective):
-                                                        // keep the barrier protocol, skip the math
-        tc_fence_before();
-        mbar_arrive(p_full);
+      if (warp_idle) {                                  // keep the barrier protocol, skip the math (an idle warp runs at
+        tc_fence_before();                              // most one tile ahead: S(j+2) needs every arrival for tile j)
+        mbar_arrive(p_full + 8 * (j & 1));
         continue;
       }
-      uint8_t* prow = smem + kOffP + row * 128;
+      uint32_t r[32];
+      tmem_ld32(tmem_S + lane_off + (uint32_t)(j & 1) * kBKV, r);
 
       if (!kMask && nvalid == kBKV) {
         // ======== fast path: full, mask-free tile (decoder self-attention): ~4.5 instructions per (query, key) ========
-        float mx = -INFINITY;
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_S + lane_off + c * 32, r);
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
-          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-        }
-        const float m_new = fmaxf(m_run, mx * p.scale_log2);       // scale > 0 (checked on the host)
-        const float corr = ex2_approx(m_run - m_new);               // m_run = -inf -> 0
-        if (j > 0) {
-          mbar_wait(o_done, (j - 1) & 1);
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, corr != 1.0f)) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + lane_off, o);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-            tmem_st32(tmem_O + lane_off, o);
-          }
-        }
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;   // scale > 0 (checked on the host)
+        // lazy rescale: keep the old reference maximum unless the new one is more than 2^8 above it
+        const bool grow = mx > m_run + 8.0f;                         // m_run = -inf on the first tile -> true
+        const float m_new = grow ? mx : m_run;
+        const float corr = grow ? ex2_approx(m_run - m_new) : 1.0f;  // m_run = -inf -> 0
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_S + lane_off + c * 32, r);
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_new));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_new));
-            l4[i & 3] += e0 + e1;
-            pk[i] = pack_bf16(e0, e1);
-          }
-          uint8_t* half = prow + (c >> 1) * kPHalfBytes;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {          // 4 x 16-byte chunks = 32 keys
-            const int chunk = (c & 1) * 4 + g;
-            *reinterpret_cast<uint4*>(half + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          }
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_new));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_new));
+          l4[i & 3] += e0 + e1;
+          pk[i] = pack_bf16(e0, e1);
         }
         l_run = fmaf(l_run, corr, (l4[0] + l4[1]) + (l4[2] + l4[3]));
         m_run = m_new;
+        sync_o(j, corr);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)              // 4 x 16-byte chunks = 32 keys
+          *reinterpret_cast<uint4*>(prow + (j & 1) * kPBytes + ((g ^ psw) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       } else {
         // ======== general path: radar mask and / or a partial last tile ========
         // ---- pass A: scaled, masked row maximum; remember which keys are allowed -------------------------
-        uint32_t allow[4] = {0u, 0u, 0u, 0u};
+        uint32_t allow = 0u;
         float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nchunks) {
-            uint32_t r[32];
-            tmem_ld32(tmem_S + lane_off + c * 32, r);
-            uint32_t bits = 0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int kk = c * 32 + i;
-              bool ok = kk < nvalid;
-              if (kMask) {
-                // cdist(mm route) < radius, evaluated on squared distances: acc < thr  (thr: smallest float whose sqrt >= r)
-                const float x = kx[kk], y = ky[kk], n = kn[kk];
-                const float dc = __fmaf_rn(1.0f, n, __fmaf_rn(cc.nrm, 1.0f, __fmaf_rn(cc.m2y, y, __fmul_rn(cc.m2x, x))));
-                const float df = __fmaf_rn(1.0f, n, __fmaf_rn(cf.nrm, 1.0f, __fmaf_rn(cf.m2y, y, __fmul_rn(cf.m2x, x))));
-                const float dr = __fmaf_rn(1.0f, n, __fmaf_rn(cr.nrm, 1.0f, __fmaf_rn(cr.m2y, y, __fmul_rn(cr.m2x, x))));
-                ok = ok && ((dc < thr) | (df < thr) | (dr < thr));
-              }
-              if (ok) {
-                bits |= 1u << i;
-                mx = fmaxf(mx, __uint_as_float(r[i]) * p.scale_log2);
-              }
-            }
-            allow[c] = bits;
+        for (int i = 0; i < 32; ++i) {
+          bool ok = i < nvalid;
+          if (kMask) {
+            // cdist(mm route) < radius, evaluated on squared distances: acc < thr  (thr: smallest float whose sqrt >= r)
+            const float x = kx[i], y = ky[i], n = kn[i];
+            const float dc = __fmaf_rn(1.0f, n, __fmaf_rn(cc.nrm, 1.0f, __fmaf_rn(cc.m2y, y, __fmul_rn(cc.m2x, x))));
+            const float df = __fmaf_rn(1.0f, n, __fmaf_rn(cf.nrm, 1.0f, __fmaf_rn(cf.m2y, y, __fmul_rn(cf.m2x, x))));
+            const float dr = __fmaf_rn(1.0f, n, __fmaf_rn(cr.nrm, 1.0f, __fmaf_rn(cr.m2y, y, __fmul_rn(cr.m2x, x))));
+            ok = ok && ((dc < thr) | (df < thr) | (dr < thr));
+          }
+          if (ok) {
+            allow |= 1u << i;
+            mx = fmaxf(mx, __uint_as_float(r[i]) * p.scale_log2);
           }
         }
         const float m_new = fmaxf(m_run, mx);
         const float corr = (m_new == -INFINITY) ? 1.0f : exp2f(m_run - m_new);      // m_run = -inf -> 0
         l_run *= corr;
-
-        // ---- O rescale (needs PV(j-1) retired; also frees the P buffer) ------------------------------------
-        if (j > 0) {
-          mbar_wait(o_done, (j - 1) & 1);
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, corr != 1.0f)) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + lane_off, o);
+        // ---- pass B: probabilities -> bf16 P in shared memory (K-major, 64B swizzle) ----------------------
+        float pv[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-            tmem_st32(tmem_O + lane_off, o);
-          }
-        }
-
-        // ---- pass B: probabilities -> bf16 P in shared memory (K-major, 128B swizzle) ----------------------
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nchunks) {
-            uint32_t r[32];
-            tmem_ld32(tmem_S + lane_off + c * 32, r);
-            float pv[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
-              pv[i] = ((allow[c] >> i) & 1u) ? e : 0.f;
-              l_run += pv[i];
-            }
-            uint8_t* half = prow + (c >> 1) * kPHalfBytes;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {          // 4 x 16-byte chunks = 32 keys
-              uint4 u;
-              u.x = pack_bf16(pv[8 * g + 0], pv[8 * g + 1]); u.y = pack_bf16(pv[8 * g + 2], pv[8 * g + 3]);
-              u.z = pack_bf16(pv[8 * g + 4], pv[8 * g + 5]); u.w = pack_bf16(pv[8 * g + 6], pv[8 * g + 7]);
-              const int chunk = (c & 1) * 4 + g;
-              *reinterpret_cast<uint4*>(half + ((chunk ^ (row & 7)) << 4)) = u;
-            }
-          }
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new);
+          pv[i] = ((allow >> i) & 1u) ? e : 0.f;
+          l_run += pv[i];
         }
         m_run = m_new;
+        sync_o(j, corr);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {          // 4 x 16-byte chunks = 32 keys
+          uint4 u;
+          u.x = pack_bf16(pv[8 * g + 0], pv[8 * g + 1]); u.y = pack_bf16(pv[8 * g + 2], pv[8 * g + 3]);
+          u.z = pack_bf16(pv[8 * g + 4], pv[8 * g + 5]); u.w = pack_bf16(pv[8 * g + 6], pv[8 * g + 7]);
+          *reinterpret_cast<uint4*>(prow + (j & 1) * kPBytes + ((g ^ psw) << 4)) = u;
+        }
       }
       fence_proxy_async_smem();                // generic-proxy smem writes -> visible to the MMA (async proxy)
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(p_full + 8 * (j & 1));
     }
 
     // ---- epilogue: O / l -> bf16 ---------------------------------------------------------------------------
     float o[32];
-    if (T > 0) {
-      mbar_wait(o_done, (T - 1) & 1);
+    if (T > 0 && !warp_idle) {
+      mbar_wait(o_done + 8 * ((T - 1) & 1), ((T - 1) >> 1) & 1);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(tmem_O + lane_off, r);
@@ -355,11 +327,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-// ---- host: 3-D tensor maps [E, L, B] with a 32 x 128 x 1 box, 64-byte swizzle ------------------------------
+// ---- host: 3-D tensor maps [E, L, B] with a 32 x rows x 1 box (rows = 128 for Q, 64 for K / V), 64-byte swizzle ------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -377,22 +349,23 @@ EncodeTiledFn encode_fn3() {
 }
 
 struct Key3 {
-  const void* ptr; long long ld, bs; int E, L, B;
-  bool operator==(const Key3& o) const { return ptr == o.ptr && ld == o.ld && bs == o.bs && E == o.E && L == o.L && B == o.B; }
+  const void* ptr; long long ld, bs; int E, L, B, rows;
+  bool operator==(const Key3& o) const { return ptr == o.ptr && ld == o.ld && bs == o.bs && E == o.E && L == o.L && B == o.B && rows == o.rows; }
 };
 struct Key3Hash {
   size_t operator()(const Key3& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.bs; h = h * 1000003u ^ (size_t)k.E;
     h = h * 1000003u ^ (size_t)k.L;
+    h = h * 1000003u ^ (size_t)k.rows;
     return h * 1000003u ^ (size_t)k.B;
   }
 };
 
-bool get_map3(const void* ptr, long long ld, long long bs, int E, int L, int B, CUtensorMap* out) {
+bool get_map3(const void* ptr, long long ld, long long bs, int E, int L, int B, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<Key3, CUtensorMap, Key3Hash> cache;
-  Key3 key{ptr, ld, bs, E, L, B};
+  Key3 key{ptr, ld, bs, E, L, B, box_rows};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
@@ -400,7 +373,7 @@ bool get_map3(const void* ptr, long long ld, long long bs, int E, int L, int B, 
   if (!fn) { set_error("tc_attention_fwd: cuTensorMapEncodeTiled entry point not available"); return false; }
   cuuint64_t dims[3] = {(cuuint64_t)E, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(B > 1 ? bs : (long long)L * ld) * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kD, (cuuint32_t)kBKV, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kD, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -431,9 +404,9 @@ bool attention_tc_supported(const tc_attention_args* a) {
 int attention_tc_launch(const tc_attention_args* a, cudaStream_t s) {
   const int E = a->heads * a->D;
   CUtensorMap mq, mk, mv;
-  if (!get_map3(a->q, a->ldq, a->q_batch_stride, E, a->Lq, a->B, &mq)) return TC_ERR_SHAPE;
-  if (!get_map3(a->k, a->ldk, a->k_batch_stride, E, a->Lk, a->B, &mk)) return TC_ERR_SHAPE;
-  if (!get_map3(a->v, a->ldv, a->v_batch_stride, E, a->Lk, a->B, &mv)) return TC_ERR_SHAPE;
+  if (!get_map3(a->q, a->ldq, a->q_batch_stride, E, a->Lq, a->B, kBQ, &mq)) return TC_ERR_SHAPE;
+  if (!get_map3(a->k, a->ldk, a->k_batch_stride, E, a->Lk, a->B, kBKV, &mk)) return TC_ERR_SHAPE;
+  if (!get_map3(a->v, a->ldv, a->v_batch_stride, E, a->Lk, a->B, kBKV, &mv)) return TC_ERR_SHAPE;
   AttnTcParams p;
   p.B = a->B; p.Lq = a->Lq; p.Lk = a->Lk; p.heads = a->heads;
   p.scale_log2 = a->scale * kLog2e;

@@ -23,8 +23,7 @@
 //     ring is full, and stores a query's channels once its last camera has been consumed.
 // (A cp.async.bulk per texel was measured first: UBLKCP takes uniform registers, so 16 per-lane copies turn into a
 // serialised ELECT/R2UR loop that cost a third of the kernel.)
-// 24 warps x 1 slot (bf16 in/out, 80 registers) or 12 warps x 2 slots (fp32 variants) x 8 KB = 192 KB of shared memory
-// per CTA, one CTA per SM.  Measured and rejected (round 1): a global atomic query counter (7200 same-address atomics
+// 12 warps x 2 slots x 8 KB = 192 KB of shared memory per CTA, one CTA per SM.  Measured and rejected (round 1): a global atomic query counter (7200 same-address atomics
 // cost more than the tail they remove) and the 16-texel weighted sum as mma.sync m16n8k16 with 3-way bf16-split weights
 // (bit-accurate, but the accumulator fragment leaves 1 lane in 4 with useful data: the per-query epilogue cost more
 // than the 192 FMA/unpack instructions it replaced; 13-17 us vs 10.5 us).
@@ -397,11 +396,12 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   const bool bi = a->feat_dtype == TC_BF16, bo = a->out_dtype == TC_BF16;
   const long long total = (long long)a->B * a->Q;
   cudaError_t e = cudaSuccess;
-  // bf16 in / bf16 out (the engine's path): 24 warps x 1 slot measured fastest (10.5 us vs 10.9 us for 12 x 2 on the
-  // bench workload, tools/k1_bench.py); the fp32 instantiations need more registers and keep 12 x 2.
+  // bf16 in / bf16 out (the engine's path): 24 warps x 1 slot is faster back to back (10.5 us vs 10.9 us for 12 x 2,
+  // tools/k1_bench.py: the launch ramp hides behind the previous launch) but slower inside the step (bracket 19.8 us vs
+  // 18.4 us, step +9 us: 768-thread CTAs start later), so 12 x 2 stays the default.
   if (bi && bo) {
-    if (sample_variant() == 1) e = launch_sample<true, true, 12, 2>(p, total, sm_count, s);
-    else e = launch_sample<true, true, 24, 1>(p, total, sm_count, s);
+    if (sample_variant() == 1) e = launch_sample<true, true, 24, 1>(p, total, sm_count, s);
+    else e = launch_sample<true, true, 12, 2>(p, total, sm_count, s);
   } else if (bi) e = launch_sample<true, false, 12, 2>(p, total, sm_count, s);
   else if (bo) e = launch_sample<false, true, 12, 2>(p, total, sm_count, s);
   else e = launch_sample<false, false, 12, 2>(p, total, sm_count, s);
