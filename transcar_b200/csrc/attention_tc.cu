@@ -43,6 +43,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// sm_100 packed / 3-input fp32 instructions (FMNMX3, FFMA2, FADD2): the fast path is bound by warp instruction issue
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// (d0, d1) = (a0, a1) * (b, b) + (c, c)
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\tmov.b64 c, {%5, %5};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+// (d0, d1) += (a0, a1)
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
+  asm("{\n\t.reg .b64 a, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 d, {%0, %1};\n\tadd.rn.f32x2 d, d, a;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+
 struct AttnTcParams {
   int B, Lq, Lk, heads;
   float scale_log2;                 // scale * log2(e)
@@ -89,7 +107,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     mbar_init(q_full, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
     mbar_init(s_full, 1); mbar_init(s_full + 8, 1);
-    mbar_init(p_full, 128); mbar_init(p_full + 8, 128);
+    mbar_init(p_full, 4); mbar_init(p_full + 8, 4);             // one arrival per softmax warp
     mbar_init(o_done, 1); mbar_init(o_done + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -182,8 +200,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint8_t* prow = smem + kOffP + row * 64;
     const int psw = (row >> 1) & 3;
 
-    // Before P(j) is written: (rarely) rescale O by this row's correction factor - PV(j-1) must have retired - and
-    // make sure PV(j-2), the last reader of P buffer j & 1, has retired (two tiles ago: never a real wait).
+    // Before P(j) is written: (rarely) rescale O by this row's correction factor - PV(j-1) must have retired.  The last
+    // reader of P buffer j & 1, PV(j-2), needs no wait: the MMA thread issued it before S(j) and tcgen05.commit tracks
+    // every earlier MMA of the thread, so s_full(j) implies it.  (A wait on an already completed mbarrier still costs
+    // ~220 cycles - measured with clock64 - which is why the softmax warps wait on exactly one barrier per tile.)
     auto sync_o = [&](int j, float corr) {
       if (j > 0 && __any_sync(0xffffffffu, corr != 1.0f)) {
         mbar_wait(o_done + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
@@ -194,7 +214,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
         tmem_st32(tmem_O + lane_off, o);
       }
-      if (j > 1) mbar_wait(o_done + 8 * (j & 1), ((j - 2) >> 1) & 1);
     };
 
     for (int j = 0; j < T; ++j) {
@@ -219,7 +238,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tc_fence_after();
       if (warp_idle) {                                  // keep the barrier protocol, skip the math (an idle warp runs at
         tc_fence_before();                              // most one tile ahead: S(j+2) needs every arrival for tile j)
-        mbar_arrive(p_full + 8 * (j & 1));
+        if (lane == 0) mbar_arrive(p_full + 8 * (j & 1));
         continue;
       }
       uint32_t r[32];
@@ -229,19 +248,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         // ======== fast path: full, mask-free tile (decoder self-attention): ~4.5 instructions per (query, key) ========
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+        for (int i = 0; i < 16; ++i) m4[i & 3] = max3(m4[i & 3], __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;   // scale > 0 (checked on the host)
         // lazy rescale: keep the old reference maximum unless the new one is more than 2^8 above it
         const bool grow = mx > m_run + 8.0f;                         // m_run = -inf on the first tile -> true
         const float m_new = grow ? mx : m_run;
         const float corr = grow ? ex2_approx(m_run - m_new) : 1.0f;  // m_run = -inf -> 0
+        const float neg_m = -m_new;
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_new));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_new));
-          l4[i & 3] += e0 + e1;
+          float e0, e1;
+          fma2(e0, e1, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m);
+          e0 = ex2_approx(e0);
+          e1 = ex2_approx(e1);
+          add2(l4[2 * (i & 1)], l4[2 * (i & 1) + 1], e0, e1);
           pk[i] = pack_bf16(e0, e1);
         }
         l_run = fmaf(l_run, corr, (l4[0] + l4[1]) + (l4[2] + l4[3]));
@@ -294,7 +316,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       fence_proxy_async_smem();                // generic-proxy smem writes -> visible to the MMA (async proxy)
       tc_fence_before();
-      mbar_arrive(p_full + 8 * (j & 1));
+      __syncwarp();                            // one arrival per warp: 128 arrivals on one mbarrier serialise
+      if (lane == 0) mbar_arrive(p_full + 8 * (j & 1));
     }
 
     // ---- epilogue: O / l -> bf16 ---------------------------------------------------------------------------

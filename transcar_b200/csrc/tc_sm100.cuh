@@ -28,8 +28,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug becomes a trap (launch error), never a hung GPU.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug becomes a trap (launch error), never a hung GPU.  The non-blocking test comes first: a
+// phase that has already completed (the common case for pipelined consumers) should not pay try_wait's suspend path.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > kSpinLimit) __trap();
