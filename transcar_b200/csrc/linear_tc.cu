@@ -37,7 +37,8 @@ constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kOffBars = kStages * kStageBytes;
 constexpr uint32_t kOffVec = kOffBars + 128;
 constexpr uint32_t kOffPart = kOffVec + 3 * BN * 4;
-constexpr uint32_t kSmemUsed = kOffPart + BM * 8;
+constexpr int kMaxCluster = 4;                        // LayerNorm rows span at most 4 CTAs (N <= 256)
+constexpr uint32_t kSmemUsed = kOffPart + kMaxCluster * BM * 8;
 constexpr size_t kSmemBytes = kSmemUsed + 1024;          // + alignment slack
 
 struct EpiParams {
@@ -97,15 +98,22 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t local_addr, uint32_t rank) {
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// LayerNorm statistics exchange between the CTAs of a cluster: every CTA PUSHES its per-row (sum, sum of squares) into
+// slot [own rank][row] of each peer's shared memory (one relaxed 64-bit store: the value is its own flag, nothing else is
+// published with it) and polls its own slots, which start as a NaN sentinel.  No cluster barrier sits on the critical path (the first version spent 41 % of its warp samples in
+// barrier.cluster arrive / wait - ncu, profiles/r01_ncu_linear.txt): the only one (sentinels written before any peer
+// may push) is split, arrive right after the init, wait just before the first push, ~5 us later.
+constexpr unsigned long long kStatSentinel = 0x7fffffff7fffffffull;        // (NaN, NaN)
+__device__ __forceinline__ void st_dsmem_u64(uint32_t local_addr, uint32_t rank, unsigned long long v) {
   uint32_t remote;
-  float2 v;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote) : "memory");
+  asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_smem_u64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
   return v;
 }
 
@@ -144,6 +152,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();            // everything above touched parameters only; activations are read from here on
+  if (kLN && warp < 2) cluster_arrive();   // these warps own no statistics slots: their share of the cluster barrier
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -194,6 +203,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool vec = p.vec != 0;
     const int ncols = min(BN, p.N - n0);
     const bool gate = (p.row_gate && row_ok) ? (p.row_gate[m] != 0) : true;
+    if (kLN) {                                                 // statistics slots of this row: empty
+      for (int r = 0; r < kMaxCluster; ++r) reinterpret_cast<unsigned long long*>(s_part)[r * BM + row] = kStatSentinel;
+      cluster_arrive();                                        // (warps 0 / 1 arrive before their roles start)
+    }
     {                                                          // column vectors of this tile (zero beyond N)
       const int j = threadIdx.x - 64;
       if (j < BN) {
@@ -335,13 +348,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
       }
-      s_part[row] = make_float2(s1, s2);
-      cluster_sync_all();                                        // #1: every CTA's partial sums are published
       const uint32_t me = cluster_ctarank(), nct = cluster_nctarank();
-      const uint32_t part_addr = smem_u32(&s_part[row]);
-      for (uint32_t r = 1; r < nct; ++r) {
-        const float2 o = ld_dsmem_f2(part_addr, (me + r) % nct);
-        s1 += o.x; s2 += o.y;
+      cluster_wait();                                            // every peer has written its sentinels (long ago)
+      if (nct > 1) {
+        const unsigned long long mine = ((unsigned long long)__float_as_uint(s2) << 32) | __float_as_uint(s1);
+        const uint32_t slot = smem_u32(&s_part[me * BM + row]);
+        for (uint32_t r = 1; r < nct; ++r) st_dsmem_u64(slot, (me + r) % nct, mine);
+        float t1 = 0.f, t2 = 0.f;                                // summed in rank order: identical statistics in every CTA
+        for (uint32_t r = 0; r < nct; ++r) {
+          float o1 = s1, o2 = s2;
+          if (r != me) {
+            const uint32_t addr = smem_u32(&s_part[r * BM + row]);
+            unsigned long long v = ld_smem_u64(addr);
+            for (uint32_t spins = 0; v == kStatSentinel && spins < kSpinLimit; ++spins) v = ld_smem_u64(addr);
+            o1 = __uint_as_float((uint32_t)v); o2 = __uint_as_float((uint32_t)(v >> 32));
+          }
+          t1 += o1; t2 += o2;
+        }
+        s1 = t1; s2 = t2;
       }
       const float inv_n = 1.0f / (float)p.N;
       const float mean = s1 * inv_n;
@@ -361,10 +385,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     tc_fence_before();
   }
-  if (kLN) {
-    if (warp < 2) cluster_sync_all();      // #1 for the producer / MMA warps
-    cluster_sync_all();                    // #2: nobody leaves while a peer may still read its partial sums
-  }
+  if (kLN && warp < 2) cluster_wait();     // completes the arrive / wait pair of these warps
+  // A CTA leaves only after it has received every peer's statistics, i.e. after the last write into its shared memory;
+  // its own pushes target CTAs that are still waiting for them.
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
