@@ -5,7 +5,7 @@
 // (~260 of 900 queries have any key at all, most of those one to five).  A dense-tile kernel
 // (attention_tc.cu / attention_simt.cu) spends all of its time on pairs whose probability is exactly zero and
 // re-derives the same mask once per head.  This kernel does the necessary work only:
-//   * one warp per (sample, query); every lane owns 8 consecutive channels of the 256-wide embedding, so a head
+//   * one warp per (sample, query), 16 queries per CTA; every lane owns 8 consecutive channels of the 256-wide embedding, so a head
 //     (32 channels) is a group of 4 lanes and all 8 heads share ONE pass over the keys;
 //   * scan: 32 keys per iteration, one key per lane, a conservative squared-distance prefilter (5 instructions);
 //     only candidates run the exact test, which is bit-identical to torch.cdist's mm route (tc_common.cuh);
@@ -17,7 +17,7 @@
 namespace tc {
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 16;
 
 struct SparseParams {
   const void* q; const void* k; const void* v;
@@ -46,7 +46,8 @@ constexpr int kKeyTile = 2048;           // keys staged in shared memory per pas
 
 template <bool kBf16In, bool kBf16Out>
 __global__ void __launch_bounds__(kWarps * 32) attention_sparse_kernel(const SparseParams p) {
-  __shared__ float s_kx[kKeyTile], s_ky[kKeyTile], s_kn[kKeyTile];
+  __shared__ float2 s_kxy[kKeyTile];
+  __shared__ float s_kn[kKeyTile];
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int b = blockIdx.y;
@@ -81,24 +82,25 @@ __global__ void __launch_bounds__(kWarps * 32) attention_sparse_kernel(const Spa
   for (int t0 = 0; t0 < p.Lk; t0 += kKeyTile) {
     const int nt = min(kKeyTile, p.Lk - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nt; i += kWarps * 32) {   // the CTA's 8 queries share one staged copy of the keys
-      const float2 xy = __ldg(keys + t0 + i);
-      s_kx[i] = xy.x; s_ky[i] = xy.y; s_kn[i] = key_norm(xy.x, xy.y);
+    const int nt32 = (nt + 31) & ~31;
+    for (int i = threadIdx.x; i < nt32; i += kWarps * 32) { // the CTA's queries share one staged copy of the keys
+      // the tail of the last 32-key group is padded with points whose squared distance overflows to +inf, so the scan
+      // needs no bounds test (8 instructions per 32 keys: LDS.64, 2 FADD, FMUL, FFMA, FSETP, VOTE, BRA)
+      const float2 xy = i < nt ? __ldg(keys + t0 + i) : make_float2(3e19f, 3e19f);
+      s_kxy[i] = xy; s_kn[i] = key_norm(xy.x, xy.y);
     }
     __syncthreads();
     if (!active) continue;
-    for (int k0 = 0; k0 < nt; k0 += 32) {
+#pragma unroll 4
+    for (int k0 = 0; k0 < nt32; k0 += 32) {
       const int key = k0 + lane;
-      float kx = 0.f, ky = 0.f;
-      bool cand = false;
-      if (key < nt) {
-        kx = s_kx[key]; ky = s_ky[key];
-        const float dx = kx - cx, dy = ky - cy;
-        cand = !(fmaf(dx, dx, dy * dy) >= bound2);
-      }
+      const float2 kxy = s_kxy[key];
+      const float kx = kxy.x, ky = kxy.y;
+      const float dx = kx - cx, dy = ky - cy;
+      const bool cand = !(fmaf(dx, dx, dy * dy) >= bound2);
       if (!__any_sync(0xffffffffu, cand)) continue;
       bool ok = false;
-      if (cand) ok = radar_allowed(cc, cf, cr, radius, kx, ky, s_kn[key]);
+      if (cand && key < nt) ok = radar_allowed(cc, cf, cr, radius, kx, ky, s_kn[key]);
       unsigned todo = __ballot_sync(0xffffffffu, ok);
       while (todo) {
         const int j = t0 + k0 + __ffs(todo) - 1;
