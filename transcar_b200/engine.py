@@ -231,7 +231,9 @@ class FusionDecoderEngine:
             if keep_all or l == self.L - 1:
                 hs.append(x32)
                 refs.append(ref)
-        self._join(0, ref, code)
+        if keep_all or not self.has_radar:
+            self._join(0, ref, code)
+        # otherwise radar_layers joins the last refinement itself, after it has queued the first query projection
         return hs, refs, x32, x16, ref, code
 
     def _position_encoder(self, p, ref):
@@ -307,14 +309,21 @@ class FusionDecoderEngine:
         reg_all = torch.empty((3, B, Q, 10), device=self.device, dtype=torch.float32)
         anchor, centre_norm = ref, True
         aux = {}
+
+        def q_proj(li, x16):       # needs only x: queued before / beside the regression head that feeds the geometry
+            q32, q16 = ops.linear(x16, self.radar_wq[li], self.radar_bq[li], want_f32=not self.bf16, want_bf16=self.bf16)
+            self._keep.extend((x16, q32, q16))
+            return (q16 if self.bf16 else q32).view(B, Q, C)
+
+        qp = q_proj(0, x16)
+        self._join(0, ref, code)                 # last decoder refinement (side branch)
         for li in range(3):
             s = ("", "_2", "_3")[li]
             m = ("", "2", "3")[li]
             lo, hi = RADIUS_CLAMP[li]
             geom = ops.radar_geometry(anchor, code, self.pc_range, lo, hi, centre_is_normalised=centre_norm)
-            w_q = self.radar_wq[li]
-            q32, q16 = ops.linear(x16, w_q, self.radar_bq[li], want_f32=not self.bf16, want_bf16=self.bf16)
-            qp = (q16 if self.bf16 else q32).view(B, Q, C)
+            if li > 0:
+                self._join(1, qp)
             att, row_any = ops.attention(qp, KV[:, :, (2 * li) * C:(2 * li + 1) * C],
                                          KV[:, :, (2 * li + 1) * C:(2 * li + 2) * C], self.heads,
                                          geom=geom, key_xy=key_xy, want_row_any=True)
@@ -322,6 +331,9 @@ class FusionDecoderEngine:
                                  row_gate=row_any.view(M), residual=x32, ln=self._ln("rf_norm2" + s))
             h = self._lin(x16, "rf_linear1" + s, feed=True, relu=True)
             x32, x16 = self._lin(h, "rf_linear2" + s, both=True, residual=x32, ln=self._ln("rf_norm3" + s))
+            if li + 1 < 3:
+                with self._branch(1):  # next layer's query projection: runs beside this layer's regression head
+                    qp_next = q_proj(li + 1, x16)
             with self._branch(0):      # classification head: independent of the regression head and of the next layer
                 c = self._lin(x16, "final_cls" + m + ".0", feed=True, ln=self._ln("final_cls" + m + ".1"), relu=True)
                 c2 = self._lin(c, "final_cls" + m + ".3", feed=True, ln=self._ln("final_cls" + m + ".4"), relu=True)
@@ -339,6 +351,8 @@ class FusionDecoderEngine:
             aux[f"radar{li}.row_any"] = row_any
             aux[f"radar{li}.geom"] = geom
             anchor, code, centre_norm = reg, reg, False
+            if li + 1 < 3:
+                qp = qp_next
         self._join(0, cls_all)
         return cls_all, reg_all, aux
 
