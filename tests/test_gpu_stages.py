@@ -115,6 +115,23 @@ def test_sample_bf16_and_layouts(ops):
     assert ops.is_channels_last_5d(conv)
 
 
+@pytest.mark.parametrize("B,Q", [(3, 37), (5, 901), (1, 1), (7, 149)])
+def test_sample_ragged_query_counts_bf16(ops, B, Q):
+    """Query counts that do not divide the per-CTA query ranges or the warp count: every (sample, query) row is handed out
+    exactly once by the in-kernel scheduler and lands in its own batch row (mask bit-exact, values at the bf16 bar)."""
+    feats, metas, ref, logits = _sampling_case(B, Q, "tiny", seed=3 + Q % 7, smooth=False)
+    l2i = torch.tensor(np.asarray([m["lidar2img"] for m in metas]), dtype=torch.float32, device=dev())
+    f16 = [f.to(dev()).to(torch.bfloat16) for f in feats]
+    cl16 = [f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3) for f in f16]
+    out = torch.full((B, Q, 256), float("nan"), device=dev(), dtype=torch.bfloat16)       # every row must be written
+    out16, mask16 = ops.sample_fwd(cl16, ref.to(dev()), l2i, logits.to(dev()), synthetic.PC_RANGE, 1600, 928,
+                                   out_dtype=torch.bfloat16, want_mask=True, out=out)
+    want, mask = _oracle_sampled_sum([f.float() for f in f16], metas, ref, logits, dev())
+    assert torch.equal(mask16.bool(), mask)
+    assert torch.isfinite(out16.float()).all()
+    torch.testing.assert_close(out16.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL)
+
+
 def test_sample_edge_cases(ops):
     feats, metas, _, _ = _sampling_case(1, 8, "tiny", seed=2, smooth=False)
     l2i = torch.tensor(np.asarray([m["lidar2img"] for m in metas]), dtype=torch.float32, device=dev())

@@ -366,7 +366,8 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   TC_REQUIRE(a->N >= 1 && a->N <= TC_MAX_CAMS && a->N * a->num_levels <= 32, TC_ERR_SHAPE,
              "tc_sample_fwd: num cams %d unsupported", a->N);
   TC_REQUIRE(a->C > 0 && a->C % 256 == 0, TC_ERR_SHAPE, "tc_sample_fwd: C must be a multiple of 256 (got %d)", a->C);
-  TC_REQUIRE(a->B >= 0 && a->Q >= 0 && (long long)a->B * a->Q < (1ll << 30), TC_ERR_SHAPE, "tc_sample_fwd: bad B/Q");
+  // B * Q < 2^22: the kernel recovers the batch index of a row with a float reciprocal (+-1 fix-up), exact in that range
+  TC_REQUIRE(a->B >= 0 && a->Q >= 0 && (long long)a->B * a->Q < (1ll << 22), TC_ERR_SHAPE, "tc_sample_fwd: bad B/Q (B * Q must be < 2^22)");
   TC_REQUIRE(aligned16(a->lidar2img), TC_ERR_ALIGN, "tc_sample_fwd: lidar2img must be 16-byte aligned");
   TC_REQUIRE(a->feat_dtype == TC_F32 || a->feat_dtype == TC_BF16, TC_ERR_DTYPE, "tc_sample_fwd: bad feat dtype");
   TC_REQUIRE(a->out_dtype == TC_F32 || a->out_dtype == TC_BF16, TC_ERR_DTYPE, "tc_sample_fwd: bad out dtype");
