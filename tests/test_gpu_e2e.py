@@ -93,6 +93,33 @@ def test_head_bf16_vs_reference_golden():
     assert_close_tail(reg, g["all_bbox_preds"], atol=2e-2, rtol=1e-2, frac=0.97, hard_atol=5.0, what="reg(bf16)")
 
 
+def test_head_vovnet_shapes_vs_oracle():
+    """BASELINE config 4 (`detr3d_vovnet_gridmask_det_final_trainval_cbgs`: FPN start_level=0, levels 232x400 ... 29x50,
+    4x the res101 texels): the whole head in fp32 parity mode and in bf16 against the oracle on the same inputs."""
+    from transcar_b200 import plugin
+    Q, B, seed = 900, 1, 7
+    sd = synthetic.make_state_dict(seed=seed, num_query=Q)
+    feats = synthetic.make_feats(seed, B, "vovnet", smooth=True)
+    metas = synthetic.make_img_metas(B, seed=seed)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = O.head_forward(sd, feats, metas)
+    for precision, atol, rtol, frac, hard in (("fp32", 5e-5, 1e-5, 0.99, None), ("bf16", 2e-2, 1e-2, 0.93, 5.0)):
+        cfg = synthetic.head_config(num_query=Q)
+        cfg["precision"] = precision
+        head = plugin.build_head(cfg)
+        head.load_state_dict(sd, strict=True)
+        head = head.cuda().eval()
+        with torch.no_grad():
+            got = head([f.cuda() for f in feats], metas)
+        torch.cuda.synchronize()
+        for k in ("all_cls_scores", "all_bbox_preds"):
+            assert_close_tail(got[k].float().cpu().numpy(), want[k].numpy(), atol=atol, rtol=rtol, frac=frac, hard_atol=hard,
+                              what=f"vovnet {precision} {k}")
+        del head
+        torch.cuda.empty_cache()
+
+
 def test_cross_atten_module_dropin():
     """`Detr3DCrossAtten.forward` with the reference signature vs the oracle's cross_atten (fp32, 1e-5)."""
     from transcar_b200 import plugin

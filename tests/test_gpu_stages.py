@@ -63,7 +63,7 @@ def _oracle_sampled_sum(feats, metas, ref, logits, device):
     return out, mask[:, 0, :, :, 0, 0]
 
 
-@pytest.mark.parametrize("config,B,Q", [("tiny", 2, 300), ("res101", 1, 900)])
+@pytest.mark.parametrize("config,B,Q", [("tiny", 2, 300), ("res101", 1, 900), ("vovnet", 1, 900)])
 def test_sample_fp32_vs_oracle(ops, config, B, Q):
     feats, metas, ref, logits = _sampling_case(B, Q, config, seed=5, smooth=False)
     l2i = torch.tensor(np.asarray([m["lidar2img"] for m in metas]), dtype=torch.float32, device=dev())
