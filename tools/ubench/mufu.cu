@@ -1,4 +1,5 @@
 // Microbenchmark: MUFU.EX2 throughput per SM (ops / clk), alone and mixed with FFMA2 / F2FP, vs warps per SM.
+// Build + run on the GPU box: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench/mufu tools/ubench/mufu.cu && tools/ubench/mufu
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int MODE>
