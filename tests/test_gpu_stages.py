@@ -357,6 +357,25 @@ def test_attention_radar_mask_in_kernel(ops, mode, algo):
         torch.testing.assert_close(out.float(), want, rtol=BF16_RTOL, atol=BF16_ATOL * 2)
 
 
+@pytest.mark.parametrize("algo", ["sparse", "simt"])
+def test_attention_nan_radar_point_is_never_attended(ops, algo):
+    """torch.cdist clamps the squared distance with clamp_min (NaN stays NaN), so a NaN radar coordinate is blocked for
+    every query (H:549-571); fmaxf(NaN, 0) = 0 would have made it the nearest point of all of them."""
+    B, Q, R, heads, E = 1, 300, 64, 8, 256
+    radar_xy, centre, code = _geometry_inputs(B, Q, R, seed=37)
+    radar_xy[0, 5, 0] = float("nan")
+    geom = ops.radar_geometry(centre.view(B * Q, 3), code.view(B * Q, 10), synthetic.PC_RANGE, 1.0, 2.0, True)
+    blocked = _oracle_blocked(O.to_metres(centre), code, radar_xy, 1.0, 2.0)
+    assert blocked[0, :, 5].all()
+    q, kv = rnd((B, Q, E), 4), rnd((B, R, 2 * E), 5)
+    out, row_any = ops.attention(q, kv[:, :, :E], kv[:, :, E:], heads, geom=geom, key_xy=radar_xy, want_row_any=True, algo=algo)
+    assert torch.equal(row_any.bool(), (~blocked).any(-1))
+    want = _oracle_mha_core(q, kv[:, :, :E], kv[:, :, E:], heads, blocked)
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+    mask, _ = ops.radar_mask(geom, radar_xy, B, Q, R)
+    assert torch.equal(mask.bool(), blocked)
+
+
 def test_attention_matches_nn_multiheadattention(ops):
     """Whole nn.MultiheadAttention (in-proj, core, out-proj) with a bool mask == the oracle's mha(), fp32."""
     sd = {k: v.to(dev()) for k, v in synthetic.make_state_dict(1, 128).items()}

@@ -118,7 +118,7 @@ __device__ __forceinline__ float cdist_mm(const Circle& c, float kx, float ky, f
   acc = __fmaf_rn(c.m2y, ky, acc);
   acc = __fmaf_rn(c.nrm, 1.0f, acc);
   acc = __fmaf_rn(1.0f, knrm, acc);
-  return __fsqrt_rn(fmaxf(acc, 0.0f));
+  return __fsqrt_rn(acc < 0.0f ? 0.0f : acc);       // clamp_min(0) as torch.cdist does it: a NaN stays NaN (never < radius)
 }
 // geom = (cx, cy, fx, fy, rx, ry, radius, -)
 __device__ __forceinline__ bool radar_allowed(const Circle& c, const Circle& f, const Circle& r, float radius,
