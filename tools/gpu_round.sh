@@ -11,5 +11,5 @@ timeout 300 python tools/step_trace.py gpurun_out/step_trace.json > gpurun_out/s
 timeout 300 python tools/k1_bench.py > gpurun_out/k1_bench.log 2>&1; tail -1 gpurun_out/k1_bench.log
 timeout 300 python tools/attn_bench.py 8 > gpurun_out/attn_bench.log 2>&1; tail -1 gpurun_out/attn_bench.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py 1 bf16 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-bash tools/gpu_ncu.sh sample:sample_kernel:2:1 attn:attention_tc:2:1 linear_ln:linear_tc_kernel.*1:6:1 linear:linear_tc_kernel.*0:6:1 attn_sparse:attention_sparse:1:1
+bash tools/gpu_ncu.sh sample:sample_kernel:2:1 attn:attention_tc:2:1 linear:linear_tc:12:9 attn_sparse:attention_sparse:1:1
 ls -la gpurun_out
