@@ -343,12 +343,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else {
       // LayerNorm over the full row: this CTA holds 64 of its N columns, the cluster holds all of them
       float s1 = 0.f, s2 = 0.f;
+      float pre[BN];                   // the pre-LayerNorm row stays in registers: the accumulator is read once
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         load_chunk(c, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+        for (int j = 0; j < 32; ++j) { pre[c * 32 + j] = v[j]; s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
       }
       const uint32_t me = cluster_ctarank(), nct = cluster_nctarank();
       cluster_wait();                                            // every peer has written its sentinels (long ago)
@@ -376,10 +377,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
-        load_chunk(c, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] = fmaf((v[j] - mean) * rstd, s_gamma[c * 32 + j], s_beta[c * 32 + j]);
+          v[j] = fmaf((pre[c * 32 + j] - mean) * rstd, s_gamma[c * 32 + j], s_beta[c * 32 + j]);
           if (p.relu) v[j] = fmaxf(v[j], 0.f);
         }
         store_chunk(c, v);
