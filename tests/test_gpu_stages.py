@@ -217,6 +217,30 @@ def test_linear_full_epilogue(ops, mode):
     assert big[:, :N].abs().sum() == 0 and big[:, 2 * N:].abs().sum() == 0
 
 
+def test_linear_layernorm_nan_rows_stay_local_and_fast(ops):
+    """The LayerNorm statistics travel between the CTAs of a cluster as (sum, sum of squares) pairs with a NaN-pattern
+    'empty' marker: rows whose sums ARE NaN (NaN residual) must neither be mistaken for the marker (a bounded spin of
+    ~40 ms per row block) nor disturb the other rows."""
+    import time
+    M, N, K = 7200, 256, 256
+    A, W, b = rnd((M, K), 4).bfloat16(), rnd((N, K), 5, K ** -0.5).bfloat16(), rnd((N,), 6, 0.1)
+    res = rnd((M, N), 8)
+    ln = (1 + 0.1 * rnd((N,), 11), 0.1 * rnd((N,), 12))
+    clean, _ = ops.linear(A, W, b, residual=res, ln=ln)
+    bad = res.clone()
+    bad[5::97, 3] = float("nan")
+    ops.linear(A, W, b, residual=bad, ln=ln)                 # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out, _ = ops.linear(A, W, b, residual=bad, ln=ln)
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 0.02, "NaN statistics were taken for the empty marker (bounded spin)"
+    nan_rows = torch.zeros(M, dtype=torch.bool, device=dev())
+    nan_rows[5::97] = True
+    assert torch.isnan(out[nan_rows]).all()
+    assert torch.equal(out[~nan_rows], clean[~nan_rows])
+
+
 def test_linear_matches_oracle_ffn_block(ops):
     """FFN + norm of a decoder layer, oracle weights (fp32 path, 1e-5)."""
     sd = {k: v.to(dev()) for k, v in synthetic.make_state_dict(1, 128).items()}

@@ -105,7 +105,8 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 // published with it) and polls its own slots, which start as a NaN sentinel.  No cluster barrier sits on the critical path (the first version spent 41 % of its warp samples in
 // barrier.cluster arrive / wait - ncu, profiles/r01_ncu_linear.txt): the only one (sentinels written before any peer
 // may push) is split, arrive right after the init, wait just before the first push, ~5 us later.
-constexpr unsigned long long kStatSentinel = 0x7fffffff7fffffffull;        // (NaN, NaN)
+// a NaN pair with a payload no arithmetic produces (sums of NaN inputs are the canonical 0x7fffffff): never a real value
+constexpr unsigned long long kStatSentinel = 0xffc0dead'ffc0deadull;
 __device__ __forceinline__ void st_dsmem_u64(uint32_t local_addr, uint32_t rank, unsigned long long v) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
@@ -342,15 +343,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     } else {
       // LayerNorm over the full row: this CTA holds 64 of its N columns, the cluster holds all of them
-      float s1 = 0.f, s2 = 0.f;
       float pre[BN];                   // the pre-LayerNorm row stays in registers: the accumulator is read once
+      float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};   // four partial sums: 16-deep dependent chains, not 64
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         load_chunk(c, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { pre[c * 32 + j] = v[j]; s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+        for (int j = 0; j < 32; ++j) { pre[c * 32 + j] = v[j]; p1[j & 3] += v[j]; p2[j & 3] = fmaf(v[j], v[j], p2[j & 3]); }
       }
+      float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
       const uint32_t me = cluster_ctarank(), nct = cluster_nctarank();
       cluster_wait();                                            // every peer has written its sentinels (long ago)
       if (nct > 1) {
