@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
     return LIB
 
