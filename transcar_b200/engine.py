@@ -17,8 +17,6 @@ accumulation, fp32 residual stream / LayerNorm / reference points / masks).
 """
 from __future__ import annotations
 
-import os
-
 import numpy as np
 import torch
 
@@ -198,12 +196,11 @@ class FusionDecoderEngine:
             x32, x16 = self._lin(att.view(M, C), p + "attentions.0.attn.out_proj", both=True,
                                  residual=x32, ln=self._ln(p + "norms.0"))
             # --- Detr3DCrossAtten (T:302-378)
-            if os.environ.get("TC_JOIN") == "early":
-                self._join(0, pos_feat, ref)
             aw = self._lin(x16, p + "attentions.1.attention_weights", bias=False,
                            row_bias=self.row_bias_aw[l], row_bias_period=Q)
-            if os.environ.get("TC_JOIN") is None:
-                self._join(0, pos_feat, ref)     # reference points refined by the previous layer + their position feature
+            # join here, between the logits and the sampling launch: before the logits (+37 us per step) or after the
+            # sampling launch (+37 us) were both measured slower
+            self._join(0, pos_feat, ref)     # reference points refined by the previous layer + their position feature
             ev = self.sample_events
             if ev is not None:          # bench.py: per-launch CUDA-event timing of K1 on the launching stream
                 e0 = torch.cuda.Event(enable_timing=True, external=self.external_events)
@@ -218,8 +215,6 @@ class FusionDecoderEngine:
                 self.cam_masks.append(cam_mask)
             if l == max(self.L - 2, 0):
                 self._start_radar_branch()
-            if os.environ.get("TC_JOIN") == "late":   # timing experiment only: K1 reads a stale ref
-                self._join(0, pos_feat, ref)
             x32, x16 = self._lin(s.view(M, C), p + "attentions.1.output_proj", both=True,
                                  residual=x32, residual2=pos_feat, ln=self._ln(p + "norms.1"))
             # --- FFN (mmcv FFN: x + W2 relu(W1 x)) + norm
