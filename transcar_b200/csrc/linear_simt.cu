@@ -2,15 +2,16 @@
 // This is the parity mode (fp32 operands, 1e-5 vs the reference) and the fallback for the tiny odd
 // shapes of the bf16 build (N = 10, 24; K = 36).  The tensor-core (tcgen05) path lives in linear_tc.cu.
 //
-// Tile: 32 rows x 256 columns per 256-thread block, K step 16.  Thread (warp w, lane l) owns rows
-// 4w..4w+3 and columns 8l..8l+7, so a full output row lives in one warp and the LayerNorm epilogue is a
+// Tile: 32 rows x (32 * CPL) columns per 256-thread block, K step 16, CPL = 8 (256 columns) or 2 (N <= 64: the first
+// radar feature layer, 36 -> 64, would leave 24 of 32 lanes idle in the wide tile).  Thread (warp w, lane l) owns rows
+// 4w..4w+3 and columns CPL*l..CPL*l+CPL-1, so a full output row lives in one warp and the LayerNorm epilogue is a
 // pair of warp reductions - no second pass over HBM.
 #include "tc_common.cuh"
 
 namespace tc {
 namespace {
 
-constexpr int BM = 32, BN = 256, BK = 16;
+constexpr int BM = 32, BK = 16;
 
 struct LinearParams {
   const void* A; long long lda;
@@ -62,8 +63,9 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* base
   return r;
 }
 
-template <typename TA, typename TW>
+template <typename TA, typename TW, int CPL>
 __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) {
+  constexpr int BN = 32 * CPL;
   __shared__ __align__(16) float As[BK][BM];
   __shared__ __align__(16) float Ws[BK][BN];
   pdl_trigger();
@@ -73,11 +75,11 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) 
   const TA* A = static_cast<const TA*>(p.A);
   const TW* W = static_cast<const TW*>(p.W);
 
-  float acc[4][8];
+  float acc[4][CPL];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < CPL; ++j) acc[i][j] = 0.f;
 
   for (int k0 = 0; k0 < p.K; k0 += BK) {
     if (tid < 128) {                        // A tile: 32 rows x 16 k
@@ -85,39 +87,48 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) 
       float4 v = load4<TA>(A, p.lda, m0 + r, p.M, k0 + kq, p.K, p.vec_a);
       As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
     }
+    if (tid < BN) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {           // W tile: 256 rows x 16 k
-      const int kq = i * 4;
-      float4 v = load4<TW>(W, p.ldw, n0 + tid, p.N, k0 + kq, p.K, p.vec_w);
-      Ws[kq + 0][tid] = v.x; Ws[kq + 1][tid] = v.y; Ws[kq + 2][tid] = v.z; Ws[kq + 3][tid] = v.w;
+      for (int i = 0; i < 4; ++i) {         // W tile: BN rows x 16 k
+        const int kq = i * 4;
+        float4 v = load4<TW>(W, p.ldw, n0 + tid, p.N, k0 + kq, p.K, p.vec_w);
+        Ws[kq + 0][tid] = v.x; Ws[kq + 1][tid] = v.y; Ws[kq + 2][tid] = v.z; Ws[kq + 3][tid] = v.w;
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(&As[k][warp * 4]);
-      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k][lane * 8]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[k][lane * 8 + 4]);
       const float av[4] = {a.x, a.y, a.z, a.w};
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float wv[CPL];
+      if (CPL == 8) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k][lane * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&Ws[k][lane * 8 + 4]);
+        wv[0] = w0.x; wv[1] = w0.y; wv[2 % CPL] = w0.z; wv[3 % CPL] = w0.w;
+        wv[4 % CPL] = w1.x; wv[5 % CPL] = w1.y; wv[6 % CPL] = w1.z; wv[7 % CPL] = w1.w;
+      } else {
+        const float2 w0 = *reinterpret_cast<const float2*>(&Ws[k][lane * 2]);
+        wv[0] = w0.x; wv[1] = w0.y;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        for (int j = 0; j < CPL; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
     __syncthreads();
   }
 
   // ---- epilogue ---------------------------------------------------------------------------------
-  const int nbase = n0 + lane * 8;
+  const int nbase = n0 + lane * CPL;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + warp * 4 + i;
     if (m >= p.M) continue;                 // warp-uniform
-    float y[8];
+    float y[CPL];
     const bool gate = p.row_gate ? (p.row_gate[m] != 0) : true;
     const float* rb = p.row_bias ? p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias : nullptr;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < CPL; ++j) {
       const int n = nbase + j;
       float v = 0.f;
       if (n < p.N) {
@@ -133,23 +144,23 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) 
     if (p.ln_gamma) {                       // whole row is inside this warp (host guarantees N <= 256)
       float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += (nbase + j < p.N) ? y[j] : 0.f;
+      for (int j = 0; j < CPL; ++j) s += (nbase + j < p.N) ? y[j] : 0.f;
       const float mean = warp_sum(s) / (float)p.N;
       float sq = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < CPL; ++j) {
         const float d = (nbase + j < p.N) ? y[j] - mean : 0.f;
         sq += d * d;
       }
       const float rstd = rsqrtf(warp_sum(sq) / (float)p.N + p.ln_eps);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < CPL; ++j) {
         const int n = nbase + j;
         if (n < p.N) y[j] = (y[j] - mean) * rstd * p.ln_gamma[n] + p.ln_beta[n];
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < CPL; ++j) {
       const int n = nbase + j;
       if (n >= p.N) continue;
       float v = p.relu ? fmaxf(y[j], 0.f) : y[j];
@@ -285,11 +296,18 @@ int linear_simt_launch(const tc_linear_args* a, cudaStream_t s) {
   const int ea = a->a_dtype == TC_BF16 ? 2 : 4, ew = a->w_dtype == TC_BF16 ? 2 : 4;
   p.vec_a = (a->K % 4 == 0) && ((a->lda * ea) % (4 * ea) == 0) && ((reinterpret_cast<uintptr_t>(a->A) % (4 * ea)) == 0);
   p.vec_w = (a->K % 4 == 0) && ((a->ldw * ew) % (4 * ew) == 0) && ((reinterpret_cast<uintptr_t>(a->W) % (4 * ew)) == 0);
-  dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN);
-  if (a->a_dtype == TC_F32 && a->w_dtype == TC_F32) launch(linear_simt_kernel<float, float>, grid, dim3(256), 0, s, 1u, p);
-  else if (a->a_dtype == TC_BF16 && a->w_dtype == TC_BF16) launch(linear_simt_kernel<__nv_bfloat16, __nv_bfloat16>, grid, dim3(256), 0, s, 1u, p);
-  else if (a->a_dtype == TC_F32 && a->w_dtype == TC_BF16) launch(linear_simt_kernel<float, __nv_bfloat16>, grid, dim3(256), 0, s, 1u, p);
-  else launch(linear_simt_kernel<__nv_bfloat16, float>, grid, dim3(256), 0, s, 1u, p);
+  // N <= 64 without LayerNorm (whose row must sit in one warp: any N <= 256 does in the wide tile, N <= 64 in the narrow one)
+  const bool narrow = a->N <= 64;
+  const int bn = narrow ? 64 : 256;
+  dim3 grid((a->M + BM - 1) / BM, (a->N + bn - 1) / bn);
+#define TC_SIMT_LAUNCH(TA, TW)                                                                          \
+  (narrow ? launch(linear_simt_kernel<TA, TW, 2>, grid, dim3(256), 0, s, 1u, p)                         \
+          : launch(linear_simt_kernel<TA, TW, 8>, grid, dim3(256), 0, s, 1u, p))
+  if (a->a_dtype == TC_F32 && a->w_dtype == TC_F32) TC_SIMT_LAUNCH(float, float);
+  else if (a->a_dtype == TC_BF16 && a->w_dtype == TC_BF16) TC_SIMT_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else if (a->a_dtype == TC_F32 && a->w_dtype == TC_BF16) TC_SIMT_LAUNCH(float, __nv_bfloat16);
+  else TC_SIMT_LAUNCH(__nv_bfloat16, float);
+#undef TC_SIMT_LAUNCH
   count_launch();
   return check_launch("tc_linear(simt)");
 }
