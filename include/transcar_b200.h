@@ -34,13 +34,18 @@ extern "C" {
 #define TC_API
 #endif
 
-#define TC_ABI_VERSION 4
+#define TC_ABI_VERSION 5
 #define TC_MAX_LEVELS 4
 #define TC_MAX_CAMS 8
 
 typedef void* tc_stream_t;                  /* cudaStream_t */
 
-typedef enum { TC_F32 = 0, TC_BF16 = 1 } tc_dtype;
+/* TC_BF16X2 ("split bf16") stores a logical [rows, cols] matrix as bf16 [rows, 2 * cols]: columns [0, cols) hold
+ * hi = bf16(x), columns [cols, 2 * cols) hold lo = bf16(x - hi) - 16 mantissa bits in two tensor-core operands.  A
+ * product of two split matrices is evaluated as hi*hi + lo*hi + hi*lo on the bf16 tensor cores with fp32 accumulation
+ * ("bf16x3", ~1e-5 relative: the parity-grade tensor-core mode; plain TC_BF16 is the single-pass mode, ~2e-3).
+ * TC_F16 (IEEE half, 11 mantissa bits) is the operand format of the dense attention core in that mode. */
+typedef enum { TC_F32 = 0, TC_BF16 = 1, TC_BF16X2 = 2, TC_F16 = 3 } tc_dtype;
 
 enum {
   TC_OK = 0,
@@ -70,8 +75,13 @@ TC_API uint64_t tc_launch_count(void);
  *   lidar2img    [B, N, 4, 4] fp32    (reference casts the float64 matrices to fp32 at T:386)
  *   attn_logits  [B, Q, N*L] fp32     output of the attention_weights Linear, index = cam*L + level
  *   out          [B, Q, C] out_dtype  sum_{cam,level} mask * sigmoid(logit) * bilinear(feat)
+ *                (fp32, bf16, or TC_BF16X2: split bf16 [B, Q, 2C], hi | lo)
  *   mask         [B, Q, N] uint8      optional (may be NULL): camera validity, bit-exact w.r.t. T:400-409
  */
+/* flags: TC_SAMPLE_ALL_CAMS = cameras that fail the validity test are sampled too (only `mask` records the test) -
+ * the un-masked return value of the reference's free function feature_sampling (T:381-422); the fused hot path
+ * (Detr3DCrossAtten) multiplies by the mask and therefore never sets it. */
+#define TC_SAMPLE_ALL_CAMS 1
 typedef struct {
   const void* feat[TC_MAX_LEVELS];
   int32_t H[TC_MAX_LEVELS];
@@ -87,6 +97,7 @@ typedef struct {
   float img_w, img_h;          /* img_metas[0]['img_shape'][0][1], [0][0] (quirk Q2) */
   void* out;
   uint8_t* mask;
+  int32_t flags;               /* TC_SAMPLE_* bits */
 } tc_sample_args;
 TC_API int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream);
 
@@ -109,10 +120,15 @@ TC_API int tc_nchw_to_nhwc(const float* src, void* dst, int32_t dst_dtype, int32
  *   Y  = LayerNorm_N(Y) * gamma + beta        if ln_gamma     (eps = ln_eps, biased variance; needs N <= 512)
  *   Y  = max(Y, 0)                            if relu
  *   Y += post_add[m, n]                       if post_add     (H:536: pos_feat + ReLU(feat))
- *   out_f32[m, n] = Y ; out_bf16[m, n] = bf16(Y)    (either may be NULL, not both)
+ *   out_f32[m, n] = Y ; out_bf16[m, n] = 16-bit copy of Y in out16_dtype    (either may be NULL, not both)
  *
  * a_dtype/w_dtype: both TC_F32 -> exact-fp32 SIMT path (parity mode);  both TC_BF16 -> tcgen05 tensor-core
- * path (K % 64 == 0, N % 16 == 0, 16-byte aligned rows) with SIMT fallback for the tiny odd shapes.
+ * path, one MMA pass (16-byte aligned rows, K >= 64) with SIMT fallback for the tiny odd shapes;  both TC_BF16X2 ->
+ * tcgen05 "bf16x3" path: A is [M, 2K], W is [N, 2K] split bf16 (lda / ldw >= 2K, K % 64 == 0), three MMA passes
+ * (hi*hi + lo*hi + hi*lo) into the same fp32 accumulator.
+ * out16_dtype selects the 16-bit output format: 0 or TC_BF16 -> bf16 [M, N];  TC_BF16X2 -> split bf16 [M, 2N]
+ * (hi at column n, lo at column N + n; ld_out_bf16 >= 2N) - the A operand of the next bf16x3 Linear;  TC_F16 -> IEEE
+ * half [M, N], saturated to +-65504 - the q/k/v operands of the dense attention core in bf16x3 mode.
  */
 typedef struct {
   const void* A;  int32_t a_dtype;  int64_t lda;      /* elements */
@@ -128,77 +144,9 @@ typedef struct {
   const float* post_add;  int64_t ld_post_add;
   float* out_f32;  int64_t ld_out_f32;
   void*  out_bf16; int64_t ld_out_bf16;
+  int32_t out16_dtype;
 } tc_linear_args;
 TC_API int tc_linear(const tc_linear_args* a, tc_stream_t stream);
-
-/* ------------------------------------------------------------------------------------------------
- * K3c  row-local Linear CHAIN: up to TC_CHAIN_MAX_STAGES dependent Linear layers evaluated for one 128-row tile per
- * CTA with every intermediate activation kept on chip (bf16 A operands in shared memory, fp32 accumulators and
- * residual stream in tensor memory).  Replaces, in one launch each, the row-local tails of the path:
- *   decoder layer  T:375-378 + mmcv FFN / norms (cfg :65-82) + T:190-203:
- *        output_proj + pos_feat + residual + LN -> FFN (256-512-256) + LN -> reg_branches[l] (3 Linear) -> ref update
- *   post-attention T:362 / mmcv MultiheadAttention out_proj: out_proj + residual + LN -> attention_weights (24 logits)
- *   radar layer    H:578-611 (and :642-668, :700-729): out_proj (row gate, quirk Q6) + LN -> FFN + LN ->
- *        final_reg* (3 Linear) + anchor add; final_cls* (Linear LN ReLU x2 -> Linear) as a second chain.
- * The chain is a small program: stage s computes  acc[s] (+)= act[a_buf] * W_s^T  (tcgen05, K <= 256, N <= 256) and an
- * epilogue routes the result: to a shared-memory activation buffer (the next stage's A operand), back to tensor memory
- * as a later stage's pre-loaded accumulator (residual), and / or to global memory.
- *
- *   stage.W        bf16 [N, K] row-major (row stride ldw elements); a sub-block of a larger weight is a stage of its own
- *                  (FFN hidden dim 512 = two (W1 half, W2 half) stage pairs accumulating into the same columns)
- *   stage.a_buf    activation buffer (0 / 1) read as A; stage 0 reads the global A [M, K] (TMA) through buffer a_buf
- *   stage.acc_col  tensor-memory column of the fp32 accumulator (multiple of 32, acc_col + N <= 512)
- *   stage.accumulate  != 0: the product is added to what the columns already hold (pre-load or earlier partial sum)
- *   stage.init     != 0: before the MMAs the accumulator is pre-loaded with
- *                  (row_gate[m] ? init_bias[n] : 0) + residual[m, n] + residual2[m, n]        (NULL terms skipped)
- *   stage.epi      TC_CHAIN_NONE  nothing (partial sum stays in tensor memory)
- *                  TC_CHAIN_ACT   y = acc + bias, optional ReLU
- *                  TC_CHAIN_LN    y = LayerNorm_N(acc + bias) * gamma + beta, optional ReLU
- *                  TC_CHAIN_OUT   N <= 32: y = acc + bias + row_bias[m % period]; optional tail (below)
- *   outputs of y   dst_buf >= 0: bf16 to activation buffer dst_buf;  keep_col >= 0: fp32 (+ fold_bias[n]) to tensor
- *                  memory columns keep_col.. (the accumulator pre-load of a later residual stage);
- *                  out_f32 / out_bf16: global [M, N]; out_f32_add[m, n] (optional) is added to the out_f32 copy only
- *                  (the next kernel's residual = this output + the position feature, T:377-378)
- *   stage.tail     TC_CHAIN_TAIL_REF_UPDATE (T:195-203): tail_out[m, 0:3] = sigmoid(y[{0,1,4}] + logit(tail_in[m, 0:3]))
- *                  TC_CHAIN_TAIL_ANCHOR_ADD (H:596-600, :664-665, :722-723): y[0:2] += anchor xy, y[4] += anchor z before
- *                  the store; anchor = tail_in[m, {tail_xy_col, tail_xy_col + 1, tail_z_col}], xy mapped from [0,1] to
- *                  metres with pc_range when tail_from_norm != 0 (z added as is: quirk Q3)
- * All fp32 row operands must be 32-byte aligned with row strides that are multiples of 8 elements.
- */
-#define TC_CHAIN_MAX_STAGES 12
-enum { TC_CHAIN_NONE = 0, TC_CHAIN_ACT = 1, TC_CHAIN_LN = 2, TC_CHAIN_OUT = 3 };
-enum { TC_CHAIN_TAIL_NONE = 0, TC_CHAIN_TAIL_REF_UPDATE = 1, TC_CHAIN_TAIL_ANCHOR_ADD = 2 };
-typedef struct {
-  const void* W; int64_t ldw;
-  int32_t K, N;
-  int32_t a_buf, acc_col, accumulate;
-  int32_t epi, relu;
-  int32_t dst_buf, keep_col;
-  int32_t init;
-  const float* init_bias;
-  const float* residual;  int64_t ld_residual;
-  const float* residual2; int64_t ld_residual2;
-  const uint8_t* row_gate;
-  const float* bias;
-  const float* ln_gamma; const float* ln_beta; float ln_eps;
-  const float* fold_bias;
-  const float* row_bias; int32_t row_bias_period; int64_t ld_row_bias;
-  float* out_f32;  int64_t ld_out_f32;
-  const float* out_f32_add; int64_t ld_out_f32_add;
-  void*  out_bf16; int64_t ld_out_bf16;
-  int32_t tail;
-  const float* tail_in; int64_t ld_tail_in;
-  float* tail_out;
-  int32_t tail_xy_col, tail_z_col, tail_from_norm;
-  float pc_range[6];
-} tc_chain_stage;
-typedef struct {
-  const void* A; int64_t lda;       /* bf16 [M, K] */
-  int32_t M, K;
-  int32_t num_stages;
-  tc_chain_stage stage[TC_CHAIN_MAX_STAGES];
-} tc_chain_args;
-TC_API int tc_linear_chain(const tc_chain_args* a, tc_stream_t stream);
 
 /* Fused 3 -> C position encoder head: Y = ReLU(LayerNorm(Linear_{3->C}(f(x)))), f = inverse_sigmoid (eps 1e-5,
  * T:17-32) when logit_input != 0 else identity.  Replaces T:377 (position_encoder[0:3]) and H:533
@@ -209,6 +157,7 @@ typedef struct {
   const float* bias;     /* [C]   */
   const float* ln_gamma; const float* ln_beta; float ln_eps;
   float* out_f32; void* out_bf16;   /* [M,C]; either may be NULL */
+  int32_t out16_dtype;              /* 0 / TC_BF16: out_bf16 is bf16 [M,C];  TC_BF16X2: split bf16 [M,2C] */
 } tc_point_embed_args;
 TC_API int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream);
 
@@ -218,8 +167,8 @@ TC_API int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream);
  * decoder self-attention (mask-free) and for H:578 / H:649 / H:707 with the radar distance mask of
  * H:549-571 built IN-KERNEL from per-query geometry (no [Q,R] mask tensor in HBM, no torch.where sync).
  *
- *   q [B, Lq, heads*D]  k, v [B, Lk, heads*D]   (dtype qkv_dtype; ld* = row stride in elements)
- *   out [B, Lq, heads*D] out_dtype
+ *   q [B, Lq, heads*D]  k, v [B, Lk, heads*D]   (dtype qkv_dtype: fp32, bf16 or fp16; ld* = row stride in elements)
+ *   out [B, Lq, heads*D] out_dtype (fp32, bf16, or TC_BF16X2: split bf16 [B, Lq, 2*heads*D], hi | lo, ldo >= 2*heads*D)
  *   geom (optional) [B, Lq, 8] fp32 = (cx, cy, fx, fy, rx, ry, radius, thr): centre / front / rear circle
  *         centres in metres, the clamped radius and thr = the smallest fp32 whose square root is >= radius
  *         (sqrt(x) < radius  <=>  x < thr) - produced by tc_radar_geometry
@@ -232,8 +181,8 @@ TC_API int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream);
  *         an explicit value that the shape/dtype does not support is TC_ERR_SHAPE / TC_ERR_DTYPE.
  */
 typedef enum {
-  TC_ATTN_AUTO = 0,     /* masked + 8x32 heads -> TC_ATTN_SPARSE; bf16 dense -> TC_ATTN_TENSOR; else TC_ATTN_SIMT */
-  TC_ATTN_TENSOR = 1,   /* tcgen05/TMA dense-tile kernel (bf16 operands), mask evaluated per 128x128 tile in-kernel */
+  TC_ATTN_AUTO = 0,     /* masked + 8x32 heads -> TC_ATTN_SPARSE; bf16 / fp16 dense -> TC_ATTN_TENSOR; else TC_ATTN_SIMT */
+  TC_ATTN_TENSOR = 1,   /* tcgen05/TMA dense-tile kernel (bf16 or fp16 operands), mask evaluated per tile in-kernel */
   TC_ATTN_SIMT = 2,     /* CUDA-core dense-tile kernel (fp32 parity mode) */
   TC_ATTN_SPARSE = 3    /* radar path: per-query key scan, only allowed (query, key) pairs are computed (needs geom) */
 } tc_attention_algo;
@@ -293,9 +242,16 @@ TC_API int tc_box_anchor_add(float* code, int64_t ld_code, const float* anchor, 
 TC_API int tc_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
                  tc_stream_t stream);
 
+/* fp32 [rows, cols] -> split bf16 [rows, 2 * cols] (TC_BF16X2: hi | lo); ld_dst >= 2 * cols. */
+TC_API int tc_cast_split(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
+                  tc_stream_t stream);
+
 /* N1  NMS-free decode on device.  Replaces C:39-90 + U:26-52: sigmoid, top-`max_num` over Q*classes,
  * denormalise (exp sizes, atan2 heading), centre-range test.  Fixed-size outputs, no host sync:
- *   boxes [B, max_num, 9], scores [B, max_num], labels [B, max_num] int32, keep [B, max_num] uint8.
+ *   boxes [B, max_num, 9], scores [B, max_num], labels [B, max_num] int32, keep [B, max_num] uint8, and / or
+ *   records [B, max_num, 12] fp32 = (9 box values, score, label, keep) - the fixed-size per-sample record that the
+ *   multi-GPU result gather ships (replaces mmdet's collect_results pickling, tools/test.py:218-223).
+ *   Either output group may be NULL (boxes / scores / labels / keep go together).
  * workspace: tc_decode_workspace_bytes(B, Q, classes) bytes. */
 typedef struct {
   const float* cls; const float* code;       /* [B,Q,classes], [B,Q,10] */
@@ -303,6 +259,7 @@ typedef struct {
   float post_center_range[6];
   float* boxes; float* scores; int32_t* labels; uint8_t* keep;
   void* workspace;
+  float* records;
 } tc_decode_args;
 TC_API int64_t tc_decode_workspace_bytes(int32_t B, int32_t Q, int32_t classes);
 TC_API int tc_decode(const tc_decode_args* a, tc_stream_t stream);

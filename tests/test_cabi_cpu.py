@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == names, "ctypes binding and header disagree"
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.tc_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.tc_abi_version() == _lib.ABI_VERSION == 5
     assert lib.tc_launch_count() >= 0
 
 
@@ -34,7 +34,7 @@ def test_struct_layouts_match_header_field_order():
     text = open(os.path.join(ROOT, "include", "transcar_b200.h")).read()
     for cname, cls in [("tc_sample_args", _lib.SampleArgs), ("tc_linear_args", _lib.LinearArgs),
                        ("tc_point_embed_args", _lib.PointEmbedArgs),
-                       ("tc_chain_stage", _lib.ChainStage), ("tc_chain_args", _lib.ChainArgs), ("tc_attention_args", _lib.AttentionArgs),
+                       ("tc_attention_args", _lib.AttentionArgs),
                        ("tc_radar_geometry_args", _lib.RadarGeometryArgs), ("tc_decode_args", _lib.DecodeArgs),
                        ("tc_layernorm_args", _lib.LayerNormArgs), ("tc_layernorm_bwd_args", _lib.LayerNormBwdArgs),
                        ("tc_attention_bwd_args", _lib.AttentionBwdArgs)]:

@@ -105,3 +105,35 @@ def test_training_step_reduces_loss_and_bucket_matches():
         losses.append(float(loss.detach()))
     assert np.isfinite(losses).all()
     assert losses[-1] < losses[0], losses
+
+
+def test_forward_train_is_stream_safe_and_keeps_the_decoder_engine():
+    """(a) the decoder's last refinement runs on a side stream - forward_train must read it after a join:
+    identical outputs with and without parallel branches, repeatedly; (b) optimizer steps on the radar head must not
+    rebuild the (frozen) decoder engine."""
+    from transcar_b200.training import trainable_names
+    Q, B, seed = 128, 2, 13
+    sd, head, feats, metas = _setup(Q, B, seed)
+    names = set(trainable_names(sd.keys()))
+    for k, p in head.named_parameters():
+        p.requires_grad_(k in names)
+    feats_c = [f.cuda() for f in feats]
+    eng = head.decoder_engine()
+    eng.use_branches = False
+    ref_out = head(feats_c, metas)
+    eng.use_branches = True
+    for _ in range(5):
+        out = head(feats_c, metas)
+        assert torch.equal(out["all_cls_scores"], ref_out["all_cls_scores"])
+        assert torch.equal(out["all_bbox_preds"], ref_out["all_bbox_preds"])
+    (out["all_cls_scores"].sum() + out["all_bbox_preds"].sum()).backward()
+    with torch.no_grad():
+        for p in head.parameters():
+            if p.requires_grad:
+                p.add_(p.grad, alpha=-1e-3)               # bumps the parameter version like optimizer.step()
+    head(feats_c, metas)
+    assert head.decoder_engine() is eng, "radar-head updates must not rebuild the decoder engine"
+    # un-frozen decoder parameters are refused, not silently left without gradient
+    head.transformer.reference_points.weight.requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="only the radar head trains"):
+        head(feats_c, metas)

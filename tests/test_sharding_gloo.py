@@ -71,6 +71,25 @@ def _worker(rank, world_size, port, n_samples, out_dir):
             torch.testing.assert_close(p.grad, want)
         torch.testing.assert_close(bucket.scalars, torch.arange(6, dtype=torch.float32) + (world_size - 1) / 2)
         assert net[0].bias.grad is None
+        # ---- second step after torch's default optimizer.zero_grad(set_to_none=True): the aliases are gone, backward
+        # allocates fresh .grad tensors - the bucket must pick them up (and not all-reduce stale zeros)
+        opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.1)
+        opt.zero_grad(set_to_none=True)
+        assert net[0].weight.grad is None
+        net(x * 2).sum().backward()
+        assert net[0].weight.grad.data_ptr() != bucket.views[0].data_ptr()
+        local = [p.grad.clone() for p in bucket.params]
+        bucket.all_reduce()
+        dist.all_gather_object(gathered, [g.tolist() for g in local])
+        for j, p in enumerate(bucket.params):
+            want = sum(torch.tensor(g[j]) for g in gathered) / world_size
+            torch.testing.assert_close(p.grad, want)
+            assert p.grad.data_ptr() == bucket.views[j].data_ptr()      # alias restored
+        # ---- third step through bucket.zero(): gradients land in the bucket again
+        opt.zero_grad(set_to_none=True)
+        bucket.zero()
+        net(x).sum().backward()
+        assert net[0].weight.grad.data_ptr() == bucket.flat.data_ptr()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -11,7 +11,7 @@ B = 8
 cfg = synthetic.head_config(900); cfg["precision"] = precision
 head = plugin.build_head(cfg); head.load_state_dict(synthetic.make_state_dict(0, 900)); head = head.cuda().eval()
 eng = head.engine()
-dt = torch.bfloat16 if precision == "bf16" else torch.float32
+dt = torch.float32 if precision == "fp32" else torch.bfloat16
 feats = [f.to(dt).cuda().permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3) for f in synthetic.make_feats(0, B, "res101", smooth=False)]
 prepared = eng.prepare_inputs(feats, synthetic.make_img_metas(B, seed=0))
 with torch.no_grad():

@@ -1,11 +1,12 @@
 """Kernel timeline of one CUDA-graph replay of the step (CUPTI through torch.profiler): start / duration / stream per
-kernel, gaps and overlap.  Usage: python tools/step_trace.py [out.json]"""
+kernel, gaps and overlap.  Usage: python tools/step_trace.py [out.json] [precision]"""
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from transcar_b200 import plugin, synthetic
 B = 8
-cfg = synthetic.head_config(900); cfg["precision"] = "bf16"
+precision = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
+cfg = synthetic.head_config(900); cfg["precision"] = precision
 head = plugin.build_head(cfg); head.load_state_dict(synthetic.make_state_dict(0, 900)); head = head.cuda().eval()
 eng = head.engine()
 feats = [f.to(torch.bfloat16).cuda().permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)

@@ -12,9 +12,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtranscar_b200.so")
 
-TC_F32, TC_BF16 = 0, 1
+TC_F32, TC_BF16, TC_BF16X2, TC_F16 = 0, 1, 2, 3
 TC_MAX_LEVELS, TC_MAX_CAMS = 4, 8
-ABI_VERSION = 4
+ABI_VERSION = 5
+TC_SAMPLE_ALL_CAMS = 1
 TC_ATTN_AUTO, TC_ATTN_TENSOR, TC_ATTN_SIMT, TC_ATTN_SPARSE = 0, 1, 2, 3
 
 _vp, _i32, _i64, _f32, _u8p = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -26,7 +27,7 @@ class SampleArgs(C.Structure):
                 ("feat_dtype", _i32), ("out_dtype", _i32),
                 ("ref", _vp), ("lidar2img", _vp), ("attn_logits", _vp),
                 ("pc_range", _f32 * 6), ("img_w", _f32), ("img_h", _f32),
-                ("out", _vp), ("mask", _vp)]
+                ("out", _vp), ("mask", _vp), ("flags", _i32)]
 
 
 class LinearArgs(C.Structure):
@@ -42,48 +43,14 @@ class LinearArgs(C.Structure):
                 ("relu", _i32),
                 ("post_add", _vp), ("ld_post_add", _i64),
                 ("out_f32", _vp), ("ld_out_f32", _i64),
-                ("out_bf16", _vp), ("ld_out_bf16", _i64)]
-
-
-TC_CHAIN_MAX_STAGES = 12
-TC_CHAIN_NONE, TC_CHAIN_ACT, TC_CHAIN_LN, TC_CHAIN_OUT = 0, 1, 2, 3
-TC_CHAIN_TAIL_NONE, TC_CHAIN_TAIL_REF_UPDATE, TC_CHAIN_TAIL_ANCHOR_ADD = 0, 1, 2
-
-
-class ChainStage(C.Structure):
-    _fields_ = [("W", _vp), ("ldw", _i64),
-                ("K", _i32), ("N", _i32),
-                ("a_buf", _i32), ("acc_col", _i32), ("accumulate", _i32),
-                ("epi", _i32), ("relu", _i32),
-                ("dst_buf", _i32), ("keep_col", _i32),
-                ("init", _i32),
-                ("init_bias", _vp),
-                ("residual", _vp), ("ld_residual", _i64),
-                ("residual2", _vp), ("ld_residual2", _i64),
-                ("row_gate", _vp),
-                ("bias", _vp),
-                ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_eps", _f32),
-                ("fold_bias", _vp),
-                ("row_bias", _vp), ("row_bias_period", _i32), ("ld_row_bias", _i64),
-                ("out_f32", _vp), ("ld_out_f32", _i64),
-                ("out_f32_add", _vp), ("ld_out_f32_add", _i64),
                 ("out_bf16", _vp), ("ld_out_bf16", _i64),
-                ("tail", _i32),
-                ("tail_in", _vp), ("ld_tail_in", _i64),
-                ("tail_out", _vp),
-                ("tail_xy_col", _i32), ("tail_z_col", _i32), ("tail_from_norm", _i32),
-                ("pc_range", _f32 * 6)]
-
-
-class ChainArgs(C.Structure):
-    _fields_ = [("A", _vp), ("lda", _i64), ("M", _i32), ("K", _i32), ("num_stages", _i32),
-                ("stage", ChainStage * TC_CHAIN_MAX_STAGES)]
+                ("out16_dtype", _i32)]
 
 
 class PointEmbedArgs(C.Structure):
     _fields_ = [("x", _vp), ("ldx", _i64), ("M", _i32), ("C", _i32), ("logit_input", _i32),
                 ("weight", _vp), ("bias", _vp), ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_eps", _f32),
-                ("out_f32", _vp), ("out_bf16", _vp)]
+                ("out_f32", _vp), ("out_bf16", _vp), ("out16_dtype", _i32)]
 
 
 class AttentionArgs(C.Structure):
@@ -111,7 +78,7 @@ class DecodeArgs(C.Structure):
                 ("B", _i32), ("Q", _i32), ("classes", _i32), ("max_num", _i32),
                 ("post_center_range", _f32 * 6),
                 ("boxes", _vp), ("scores", _vp), ("labels", _vp), ("keep", _vp),
-                ("workspace", _vp)]
+                ("workspace", _vp), ("records", _vp)]
 
 
 class LayerNormArgs(C.Structure):
@@ -150,7 +117,6 @@ SYMBOLS = {
     "tc_sample_fwd": (C.c_int, [C.POINTER(SampleArgs), _vp]),
     "tc_nchw_to_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tc_linear": (C.c_int, [C.POINTER(LinearArgs), _vp]),
-    "tc_linear_chain": (C.c_int, [C.POINTER(ChainArgs), _vp]),
     "tc_point_embed": (C.c_int, [C.POINTER(PointEmbedArgs), _vp]),
     "tc_attention_fwd": (C.c_int, [C.POINTER(AttentionArgs), _vp]),
     "tc_radar_geometry": (C.c_int, [C.POINTER(RadarGeometryArgs), _vp]),
@@ -158,6 +124,7 @@ SYMBOLS = {
     "tc_ref_update": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp]),
     "tc_box_anchor_add": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, C.POINTER(_f32 * 6), _i32, _vp]),
     "tc_cast_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "tc_cast_split": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "tc_decode_workspace_bytes": (C.c_int64, [_i32, _i32, _i32]),
     "tc_decode": (C.c_int, [C.POINTER(DecodeArgs), _vp]),
     "tc_transpose": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _vp]),

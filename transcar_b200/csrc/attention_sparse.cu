@@ -26,6 +26,7 @@ struct SparseParams {
   float scale;
   const float* geom; const float* key_xy;
   void* out; long long ldo;
+  int out_split;          // 16-bit output is split bf16 [.., 2*256]: hi | lo
   uint8_t* row_any;
 };
 
@@ -146,6 +147,14 @@ __global__ void __launch_bounds__(kWarps * 32) attention_sparse_kernel(const Spa
     u.x = pack_bf16(acc[0] * inv, acc[1] * inv); u.y = pack_bf16(acc[2] * inv, acc[3] * inv);
     u.z = pack_bf16(acc[4] * inv, acc[5] * inv); u.w = pack_bf16(acc[6] * inv, acc[7] * inv);
     *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + oo) = u;
+    if (p.out_split) {
+      uint4 l;
+      l.x = pack_bf16(acc[0] * inv - bf16_lo(u.x), acc[1] * inv - bf16_hi(u.x));
+      l.y = pack_bf16(acc[2] * inv - bf16_lo(u.y), acc[3] * inv - bf16_hi(u.y));
+      l.z = pack_bf16(acc[4] * inv - bf16_lo(u.z), acc[5] * inv - bf16_hi(u.z));
+      l.w = pack_bf16(acc[6] * inv - bf16_lo(u.w), acc[7] * inv - bf16_hi(u.w));
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + oo + 256) = l;
+    }
   } else {
     float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + oo);
     o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
@@ -157,7 +166,7 @@ __global__ void __launch_bounds__(kWarps * 32) attention_sparse_kernel(const Spa
 }  // namespace
 
 bool attention_sparse_supported(const tc_attention_args* a) {
-  return a->geom != nullptr && a->heads * a->D == 256 && a->D == 32;
+  return a->geom != nullptr && a->heads * a->D == 256 && a->D == 32 && (a->qkv_dtype == TC_F32 || a->qkv_dtype == TC_BF16);
 }
 
 int attention_sparse_launch(const tc_attention_args* a, cudaStream_t s) {
@@ -168,8 +177,9 @@ int attention_sparse_launch(const tc_attention_args* a, cudaStream_t s) {
   p.B = a->B; p.Lq = a->Lq; p.Lk = a->Lk;
   p.scale = a->scale; p.geom = a->geom; p.key_xy = a->key_xy;
   p.out = a->out; p.ldo = a->ldo; p.row_any = a->row_any;
+  p.out_split = a->out_dtype == TC_BF16X2 ? 1 : 0;
   dim3 grid((a->Lq + kWarps - 1) / kWarps, a->B);
-  const bool bi = a->qkv_dtype == TC_BF16, bo = a->out_dtype == TC_BF16;
+  const bool bi = a->qkv_dtype == TC_BF16, bo = a->out_dtype == TC_BF16 || a->out_dtype == TC_BF16X2;
   if (bi && bo) launch(attention_sparse_kernel<true, true>, grid, dim3(kWarps * 32), 0, s, 1u, p);
   else if (bi) launch(attention_sparse_kernel<true, false>, grid, dim3(kWarps * 32), 0, s, 1u, p);
   else if (bo) launch(attention_sparse_kernel<false, true>, grid, dim3(kWarps * 32), 0, s, 1u, p);

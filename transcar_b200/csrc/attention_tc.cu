@@ -1,4 +1,7 @@
-// K4 tensor-core path: softmax(scale * Q K^T + mask) V for head dim 32, bf16 operands, fp32 accumulation.
+// K4 tensor-core path: softmax(scale * Q K^T + mask) V for head dim 32, bf16 or fp16 operands, fp32 accumulation.
+// (fp16 - 11 mantissa bits for q, k, v and P - is the operand format of the bf16x3 precision mode: an end-to-end
+// emulation showed 11-bit attention operands keep the decoder within 1e-3 / 1e-2 of the fp32 reference where 8-bit
+// ones do not; the cost is identical, A and B only have to share one 16-bit format.)
 //
 // One CTA = 128 queries of one (sample, head); keys/values stream through a 6-stage TMA ring in 32-key tiles.
 //   S  = Q K^T   tcgen05.mma 128x32x16 (x2), both operands K-major SWIZZLE_64B, accumulator double-buffered in TMEM
@@ -20,6 +23,7 @@
 // warps per scheduler cannot hide the per-instruction latency); 64-key tiles, single S, 4 CTAs / SM: 36 us (XU 47 %: the
 // warps wait for the S round trip half of the time).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -61,12 +65,20 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
       : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
 
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) { return kF16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+
 struct AttnTcParams {
   int B, Lq, Lk, heads;
   float scale_log2;                 // scale * log2(e)
   const float* geom;                // [B, Lq, 8] or null
   const float* key_xy;              // [B, Lk, 2]
   __nv_bfloat16* out; long long ldo;
+  int out_split;                    // out is split bf16 [B, Lq, 2 * heads * 32]: hi | lo
   uint8_t* row_any;
 };
 
@@ -82,7 +94,7 @@ constexpr uint32_t kSmemBytes = kSmemUsed + 1024;               // + slack for t
 constexpr uint32_t kTmemCols = 128;                             // S0 [0,32), S1 [32,64), O [64,96); 4 CTAs x 128 = all 512 columns
 static_assert(kOffP % 512 == 0 && kPBytes % 512 == 0, "SWIZZLE_64B tile alignment");
 
-template <bool kMask>
+template <bool kMask, bool kF16>
 __global__ void __launch_bounds__(kThreads, kMask ? 2 : 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const AttnTcParams p) {
@@ -139,9 +151,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     // ===== MMA issuer =====
     if (lane == 0 && T > 0) {
       // kind::f16 descriptors: D=F32, A=B=BF16; S: M=128,N=64 (both K-major); O: M=128,N=32, B MN-major (bit 16)
-      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBKV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t kFmt = kF16 ? 0u : ((1u << 7) | (1u << 10));     // A / B format: 0 = F16, 1 = BF16
+      constexpr uint32_t idesc_s = (1u << 4) | kFmt | ((uint32_t)(kBKV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // (A and B must share one 16-bit format: an FP16 P against a BF16 V is rejected as an illegal instruction - measured.)
-      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | kFmt | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t dq = make_desc_sw64_kmajor(sbase + kOffQ);
       auto issue_s = [&](int j) {                 // S(j) -> S buffer j & 1 (free: softmax(j - 2) has arrived on p_full)
         const int s = j % kStages;
@@ -264,7 +277,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           e0 = ex2_approx(e0);
           e1 = ex2_approx(e1);
           add2(l4[2 * (i & 1)], l4[2 * (i & 1) + 1], e0, e1);
-          pk[i] = pack_bf16(e0, e1);
+          pk[i] = pack16<kF16>(e0, e1);
         }
         l_run = fmaf(l_run, corr, (l4[0] + l4[1]) + (l4[2] + l4[3]));
         m_run = m_new;
@@ -309,8 +322,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int g = 0; g < 4; ++g) {          // 4 x 16-byte chunks = 32 keys
           uint4 u;
-          u.x = pack_bf16(pv[8 * g + 0], pv[8 * g + 1]); u.y = pack_bf16(pv[8 * g + 2], pv[8 * g + 3]);
-          u.z = pack_bf16(pv[8 * g + 4], pv[8 * g + 5]); u.w = pack_bf16(pv[8 * g + 6], pv[8 * g + 7]);
+          u.x = pack16<kF16>(pv[8 * g + 0], pv[8 * g + 1]); u.y = pack16<kF16>(pv[8 * g + 2], pv[8 * g + 3]);
+          u.z = pack16<kF16>(pv[8 * g + 4], pv[8 * g + 5]); u.w = pack16<kF16>(pv[8 * g + 6], pv[8 * g + 7]);
           *reinterpret_cast<uint4*>(prow + (j & 1) * kPBytes + ((g ^ psw) << 4)) = u;
         }
       }
@@ -342,6 +355,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         u.x = pack_bf16(o[8 * g + 0], o[8 * g + 1]); u.y = pack_bf16(o[8 * g + 2], o[8 * g + 3]);
         u.z = pack_bf16(o[8 * g + 4], o[8 * g + 5]); u.w = pack_bf16(o[8 * g + 6], o[8 * g + 7]);
         dst[g] = u;
+        if (p.out_split) {
+          uint4 l;
+          l.x = pack_bf16(o[8 * g + 0] - bf16_lo(u.x), o[8 * g + 1] - bf16_hi(u.x));
+          l.y = pack_bf16(o[8 * g + 2] - bf16_lo(u.y), o[8 * g + 3] - bf16_hi(u.y));
+          l.z = pack_bf16(o[8 * g + 4] - bf16_lo(u.z), o[8 * g + 5] - bf16_hi(u.z));
+          l.w = pack_bf16(o[8 * g + 6] - bf16_lo(u.w), o[8 * g + 7] - bf16_hi(u.w));
+          dst[g + p.heads * 4] = l;          // + heads * 32 elements = heads * 4 uint4
+        }
       }
       if (p.row_any && h == 0) p.row_any[(long long)b * p.Lq + q] = l_run > 0.f ? 1 : 0;
     }
@@ -372,8 +393,8 @@ EncodeTiledFn encode_fn3() {
 }
 
 struct Key3 {
-  const void* ptr; long long ld, bs; int E, L, B, rows;
-  bool operator==(const Key3& o) const { return ptr == o.ptr && ld == o.ld && bs == o.bs && E == o.E && L == o.L && B == o.B && rows == o.rows; }
+  const void* ptr; long long ld, bs; int E, L, B, rows, f16;
+  bool operator==(const Key3& o) const { return ptr == o.ptr && ld == o.ld && bs == o.bs && E == o.E && L == o.L && B == o.B && rows == o.rows && f16 == o.f16; }
 };
 struct Key3Hash {
   size_t operator()(const Key3& k) const {
@@ -385,10 +406,10 @@ struct Key3Hash {
   }
 };
 
-bool get_map3(const void* ptr, long long ld, long long bs, int E, int L, int B, int box_rows, CUtensorMap* out) {
+bool get_map3(const void* ptr, long long ld, long long bs, int E, int L, int B, int box_rows, bool f16, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<Key3, CUtensorMap, Key3Hash> cache;
-  Key3 key{ptr, ld, bs, E, L, B, box_rows};
+  Key3 key{ptr, ld, bs, E, L, B, box_rows, f16 ? 1 : 0};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
@@ -399,7 +420,7 @@ bool get_map3(const void* ptr, long long ld, long long bs, int E, int L, int B, 
   cuuint32_t box[3] = {(cuuint32_t)kD, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("tc_attention_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
@@ -414,7 +435,9 @@ bool get_map3(const void* ptr, long long ld, long long bs, int E, int L, int B, 
 bool attention_tc_supported(const tc_attention_args* a) {
   static const bool disabled = getenv("TC_DISABLE_TC_ATTENTION") != nullptr;     // debugging / A-B measurements
   if (disabled) return false;
-  if (a->qkv_dtype != TC_BF16 || a->out_dtype != TC_BF16) return false;
+  if (a->qkv_dtype != TC_BF16 && a->qkv_dtype != TC_F16) return false;
+  if (a->out_dtype != TC_BF16 && a->out_dtype != TC_BF16X2) return false;
+  if (a->out_dtype == TC_BF16X2 && a->ldo < 2 * (long long)a->heads * a->D) return false;
   if (a->D != kD || a->Lk <= 0 || !(a->scale > 0.f)) return false;
   const int E = a->heads * a->D;
   (void)E;
@@ -427,27 +450,33 @@ bool attention_tc_supported(const tc_attention_args* a) {
 int attention_tc_launch(const tc_attention_args* a, cudaStream_t s) {
   const int E = a->heads * a->D;
   CUtensorMap mq, mk, mv;
-  if (!get_map3(a->q, a->ldq, a->q_batch_stride, E, a->Lq, a->B, kBQ, &mq)) return TC_ERR_SHAPE;
-  if (!get_map3(a->k, a->ldk, a->k_batch_stride, E, a->Lk, a->B, kBKV, &mk)) return TC_ERR_SHAPE;
-  if (!get_map3(a->v, a->ldv, a->v_batch_stride, E, a->Lk, a->B, kBKV, &mv)) return TC_ERR_SHAPE;
+  const bool f16 = a->qkv_dtype == TC_F16;
+  if (!get_map3(a->q, a->ldq, a->q_batch_stride, E, a->Lq, a->B, kBQ, f16, &mq)) return TC_ERR_SHAPE;
+  if (!get_map3(a->k, a->ldk, a->k_batch_stride, E, a->Lk, a->B, kBKV, f16, &mk)) return TC_ERR_SHAPE;
+  if (!get_map3(a->v, a->ldv, a->v_batch_stride, E, a->Lk, a->B, kBKV, f16, &mv)) return TC_ERR_SHAPE;
   AttnTcParams p;
   p.B = a->B; p.Lq = a->Lq; p.Lk = a->Lk; p.heads = a->heads;
   p.scale_log2 = a->scale * kLog2e;
   p.geom = a->geom; p.key_xy = a->key_xy;
   p.out = static_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
+  p.out_split = a->out_dtype == TC_BF16X2 ? 1 : 0;
   p.row_any = a->row_any;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { set_error("tc_attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
   static_assert(kSmemUsed + 1024 <= kSmemBytes, "shared-memory carve-up exceeds the request");
   dim3 grid((a->Lq + kBQ - 1) / kBQ, a->heads, a->B);
-  cudaError_t le = a->geom ? launch(attention_tc_kernel<true>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p)
-                           : launch(attention_tc_kernel<false>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p);
+  cudaError_t le;
+  if (f16) le = a->geom ? launch(attention_tc_kernel<true, true>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p)
+                        : launch(attention_tc_kernel<false, true>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p);
+  else le = a->geom ? launch(attention_tc_kernel<true, false>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p)
+                    : launch(attention_tc_kernel<false, false>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p);
   if (le != cudaSuccess) { set_error("tc_attention_fwd(tcgen05): %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return (int)le; }
   count_launch();
   return check_launch("tc_attention_fwd(tcgen05)");

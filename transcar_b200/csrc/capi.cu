@@ -72,14 +72,20 @@ extern "C" int tc_linear(const tc_linear_args* a, tc_stream_t stream) {
   TC_REQUIRE(a->A && a->W, TC_ERR_NULL, "tc_linear: A or W is NULL");
   TC_REQUIRE(a->out_f32 || a->out_bf16, TC_ERR_NULL, "tc_linear: no output pointer");
   TC_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, TC_ERR_SHAPE, "tc_linear: bad M/N/K %d/%d/%d", a->M, a->N, a->K);
-  TC_REQUIRE(a->lda >= a->K && a->ldw >= a->K, TC_ERR_SHAPE, "tc_linear: leading dimension smaller than K");
-  TC_REQUIRE((a->a_dtype == TC_F32 || a->a_dtype == TC_BF16) && (a->w_dtype == TC_F32 || a->w_dtype == TC_BF16),
+  const bool split_a = a->a_dtype == TC_BF16X2, split_w = a->w_dtype == TC_BF16X2;
+  TC_REQUIRE((a->a_dtype == TC_F32 || a->a_dtype == TC_BF16 || split_a) && (a->w_dtype == TC_F32 || a->w_dtype == TC_BF16 || split_w),
              TC_ERR_DTYPE, "tc_linear: bad dtype");
+  TC_REQUIRE(split_a == split_w, TC_ERR_DTYPE, "tc_linear: split bf16 (TC_BF16X2) operands come in pairs");
+  TC_REQUIRE(a->lda >= (split_a ? 2 : 1) * (int64_t)a->K && a->ldw >= (split_w ? 2 : 1) * (int64_t)a->K, TC_ERR_SHAPE,
+             "tc_linear: leading dimension smaller than K (2K for split operands)");
+  TC_REQUIRE(a->out16_dtype == 0 || a->out16_dtype == TC_BF16 || a->out16_dtype == TC_BF16X2 || a->out16_dtype == TC_F16,
+             TC_ERR_DTYPE, "tc_linear: bad out16_dtype %d", a->out16_dtype);
   TC_REQUIRE(!a->ln_gamma || a->ln_beta, TC_ERR_NULL, "tc_linear: ln_gamma without ln_beta");
   TC_REQUIRE(!a->ln_gamma || a->N <= 256, TC_ERR_SHAPE, "tc_linear: fused LayerNorm needs N <= 256 (got %d)", a->N);
   TC_REQUIRE(!a->row_bias || a->row_bias_period > 0, TC_ERR_SHAPE, "tc_linear: row_bias needs a positive period");
   TC_REQUIRE(!a->out_f32 || a->ld_out_f32 >= a->N, TC_ERR_SHAPE, "tc_linear: ld_out_f32 < N");
-  TC_REQUIRE(!a->out_bf16 || a->ld_out_bf16 >= a->N, TC_ERR_SHAPE, "tc_linear: ld_out_bf16 < N");
+  TC_REQUIRE(!a->out_bf16 || a->ld_out_bf16 >= (a->out16_dtype == TC_BF16X2 ? 2 : 1) * (int64_t)a->N, TC_ERR_SHAPE,
+             "tc_linear: ld_out_bf16 < N (2N for a split output)");
   if (a->M == 0) return TC_OK;
   cudaStream_t s = as_stream(stream);
   if (linear_tc_supported(a)) return linear_tc_launch(a, s);
@@ -93,14 +99,16 @@ extern "C" int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream) 
   TC_REQUIRE(a->D == 32, TC_ERR_SHAPE, "tc_attention_fwd: head dim must be 32 (got %d)", a->D);
   TC_REQUIRE(a->B >= 0 && a->Lq >= 0 && a->Lk >= 0 && a->heads > 0 && a->B <= 65535 && a->heads <= 65535,
              TC_ERR_SHAPE, "tc_attention_fwd: bad shape");
-  TC_REQUIRE(a->qkv_dtype == TC_F32 || a->qkv_dtype == TC_BF16, TC_ERR_DTYPE, "tc_attention_fwd: bad qkv dtype");
-  TC_REQUIRE(a->out_dtype == TC_F32 || a->out_dtype == TC_BF16, TC_ERR_DTYPE, "tc_attention_fwd: bad out dtype");
+  TC_REQUIRE(a->qkv_dtype == TC_F32 || a->qkv_dtype == TC_BF16 || a->qkv_dtype == TC_F16, TC_ERR_DTYPE,
+             "tc_attention_fwd: bad qkv dtype");
+  TC_REQUIRE(a->out_dtype == TC_F32 || a->out_dtype == TC_BF16 || a->out_dtype == TC_BF16X2, TC_ERR_DTYPE,
+             "tc_attention_fwd: bad out dtype");
   TC_REQUIRE((a->geom == nullptr) == (a->key_xy == nullptr), TC_ERR_NULL,
              "tc_attention_fwd: geom and key_xy must be given together");
   const int64_t hd = (int64_t)a->heads * a->D;
   TC_REQUIRE(a->ldq >= hd && a->ldk >= hd && a->ldv >= hd && a->ldo >= hd, TC_ERR_SHAPE,
              "tc_attention_fwd: leading dimension smaller than heads*D");
-  const int es = a->qkv_dtype == TC_BF16 ? 2 : 4, eo = a->out_dtype == TC_BF16 ? 2 : 4;
+  const int es = a->qkv_dtype == TC_F32 ? 4 : 2, eo = a->out_dtype == TC_F32 ? 4 : 2;
   TC_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->out) &&
                  (a->ldq * es) % 16 == 0 && (a->ldk * es) % 16 == 0 && (a->ldv * es) % 16 == 0 &&
                  (a->ldo * eo) % 16 == 0 && (a->q_batch_stride * es) % 16 == 0 && (a->k_batch_stride * es) % 16 == 0 &&
@@ -119,11 +127,15 @@ extern "C" int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream) 
       TC_REQUIRE(attention_tc_supported(a), TC_ERR_DTYPE, "tc_attention_fwd: tensor-core path needs bf16 q/k/v/out");
       return attention_tc_launch(a, s);
     case TC_ATTN_SIMT:
+      TC_REQUIRE(a->qkv_dtype != TC_F16 && a->out_dtype != TC_BF16X2, TC_ERR_DTYPE,
+                 "tc_attention_fwd: the SIMT path takes fp32 / bf16 operands and outputs");
       return attention_simt_launch(a, s);
     default:
       break;
   }
   if (attention_sparse_supported(a)) return attention_sparse_launch(a, s);
   if (attention_tc_supported(a)) return attention_tc_launch(a, s);
+  TC_REQUIRE(a->qkv_dtype != TC_F16 && a->out_dtype != TC_BF16X2, TC_ERR_DTYPE,
+             "tc_attention_fwd: fp16 operands / split bf16 output need the tensor-core or sparse path");
   return attention_simt_launch(a, s);
 }

@@ -6,6 +6,8 @@
 // radar feature layer, 36 -> 64, would leave 24 of 32 lanes idle in the wide tile).  Thread (warp w, lane l) owns rows
 // 4w..4w+3 and columns CPL*l..CPL*l+CPL-1, so a full output row lives in one warp and the LayerNorm epilogue is a
 // pair of warp reductions - no second pass over HBM.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace tc {
@@ -27,6 +29,7 @@ struct LinearParams {
   const float* post_add; long long ld_post_add;
   float* out_f32; long long ld_out_f32;
   __nv_bfloat16* out_bf16; long long ld_out_bf16;
+  int out16;             // TC_BF16, TC_BF16X2 (hi at column n, lo at column N + n) or TC_F16
   int vec_a, vec_w;      // 1: rows are 16-byte (fp32) / 8-byte (bf16) aligned and K % 4 == 0
 };
 
@@ -61,6 +64,16 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* base
   if (k + 2 < K) r.z = __bfloat162float(p[2]);
   if (k + 3 < K) r.w = __bfloat162float(p[3]);
   return r;
+}
+
+// split bf16 operand ([rows, 2K]: hi | lo): the value is hi + lo
+struct SplitBf16 {};
+template <>
+__device__ __forceinline__ float4 load4<SplitBf16>(const SplitBf16* base, long long ld, int row, int rows, int k, int K, int vec) {
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base);
+  const float4 hi = load4<__nv_bfloat16>(b, ld, row, rows, k, K, vec);
+  const float4 lo = load4<__nv_bfloat16>(b + K, ld, row, rows, k, K, vec);
+  return make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
 }
 
 template <typename TA, typename TW, int CPL>
@@ -166,7 +179,16 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) 
       float v = p.relu ? fmaxf(y[j], 0.f) : y[j];
       if (p.post_add) v += p.post_add[(long long)m * p.ld_post_add + n];
       if (p.out_f32) p.out_f32[(long long)m * p.ld_out_f32 + n] = v;
-      if (p.out_bf16) p.out_bf16[(long long)m * p.ld_out_bf16 + n] = __float2bfloat16_rn(v);
+      if (p.out_bf16) {
+        __nv_bfloat16* d16 = p.out_bf16 + (long long)m * p.ld_out_bf16 + n;
+        if (p.out16 == TC_F16) {
+          *reinterpret_cast<__half*>(d16) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        } else {
+          const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+          *d16 = hi;
+          if (p.out16 == TC_BF16X2) d16[p.N] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
+      }
     }
   }
 }
@@ -175,7 +197,7 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) 
 struct PointEmbedParams {
   const float* x; long long ldx; int M, C, logit;
   const float* weight; const float* bias; const float* gamma; const float* beta; float eps;
-  float* out_f32; __nv_bfloat16* out_bf16;
+  float* out_f32; __nv_bfloat16* out_bf16; int split;
 };
 
 constexpr int kPeMaxPerLane = 32;   // C <= 1024
@@ -211,7 +233,15 @@ __global__ void __launch_bounds__(128) point_embed_kernel(const PointEmbedParams
       const int c = j * 32 + lane;
       const float v = fmaxf((y[j] - mean) * rstd * p.gamma[c] + p.beta[c], 0.f);
       if (p.out_f32) p.out_f32[(long long)m * p.C + c] = v;
-      if (p.out_bf16) p.out_bf16[(long long)m * p.C + c] = __float2bfloat16_rn(v);
+      if (p.out_bf16) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        if (p.split) {
+          p.out_bf16[(long long)m * 2 * p.C + c] = hi;
+          p.out_bf16[(long long)m * 2 * p.C + p.C + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        } else {
+          p.out_bf16[(long long)m * p.C + c] = hi;
+        }
+      }
     }
   }
 }
@@ -271,7 +301,15 @@ __global__ void __launch_bounds__(256) point_embed256_kernel(const PointEmbedPar
     if (p.out_bf16) {
       uint4 u;
       u.x = pack_bf16(y[0], y[1]); u.y = pack_bf16(y[2], y[3]); u.z = pack_bf16(y[4], y[5]); u.w = pack_bf16(y[6], y[7]);
-      *reinterpret_cast<uint4*>(p.out_bf16 + (long long)m * 256 + c0) = u;
+      if (p.split) {              // [M, 512] = hi | lo
+        *reinterpret_cast<uint4*>(p.out_bf16 + (long long)m * 512 + c0) = u;
+        uint4 l;
+        l.x = pack_bf16(y[0] - bf16_lo(u.x), y[1] - bf16_hi(u.x)); l.y = pack_bf16(y[2] - bf16_lo(u.y), y[3] - bf16_hi(u.y));
+        l.z = pack_bf16(y[4] - bf16_lo(u.z), y[5] - bf16_hi(u.z)); l.w = pack_bf16(y[6] - bf16_lo(u.w), y[7] - bf16_hi(u.w));
+        *reinterpret_cast<uint4*>(p.out_bf16 + (long long)m * 512 + 256 + c0) = l;
+      } else {
+        *reinterpret_cast<uint4*>(p.out_bf16 + (long long)m * 256 + c0) = u;
+      }
     }
   }
 }
@@ -293,7 +331,8 @@ int linear_simt_launch(const tc_linear_args* a, cudaStream_t s) {
   p.post_add = a->post_add; p.ld_post_add = a->ld_post_add;
   p.out_f32 = a->out_f32; p.ld_out_f32 = a->ld_out_f32;
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); p.ld_out_bf16 = a->ld_out_bf16;
-  const int ea = a->a_dtype == TC_BF16 ? 2 : 4, ew = a->w_dtype == TC_BF16 ? 2 : 4;
+  p.out16 = a->out16_dtype == 0 ? TC_BF16 : a->out16_dtype;
+  const int ea = a->a_dtype == TC_F32 ? 4 : 2, ew = a->w_dtype == TC_F32 ? 4 : 2;
   p.vec_a = (a->K % 4 == 0) && ((a->lda * ea) % (4 * ea) == 0) && ((reinterpret_cast<uintptr_t>(a->A) % (4 * ea)) == 0);
   p.vec_w = (a->K % 4 == 0) && ((a->ldw * ew) % (4 * ew) == 0) && ((reinterpret_cast<uintptr_t>(a->W) % (4 * ew)) == 0);
   // N <= 64 without LayerNorm (whose row must sit in one warp: any N <= 256 does in the wide tile, N <= 64 in the narrow one)
@@ -303,7 +342,8 @@ int linear_simt_launch(const tc_linear_args* a, cudaStream_t s) {
 #define TC_SIMT_LAUNCH(TA, TW)                                                                          \
   (narrow ? launch(linear_simt_kernel<TA, TW, 2>, grid, dim3(256), 0, s, 1u, p)                         \
           : launch(linear_simt_kernel<TA, TW, 8>, grid, dim3(256), 0, s, 1u, p))
-  if (a->a_dtype == TC_F32 && a->w_dtype == TC_F32) TC_SIMT_LAUNCH(float, float);
+  if (a->a_dtype == TC_BF16X2 && a->w_dtype == TC_BF16X2) TC_SIMT_LAUNCH(SplitBf16, SplitBf16);
+  else if (a->a_dtype == TC_F32 && a->w_dtype == TC_F32) TC_SIMT_LAUNCH(float, float);
   else if (a->a_dtype == TC_BF16 && a->w_dtype == TC_BF16) TC_SIMT_LAUNCH(__nv_bfloat16, __nv_bfloat16);
   else if (a->a_dtype == TC_F32 && a->w_dtype == TC_BF16) TC_SIMT_LAUNCH(float, __nv_bfloat16);
   else TC_SIMT_LAUNCH(__nv_bfloat16, float);
@@ -323,7 +363,7 @@ extern "C" int tc_point_embed(const tc_point_embed_args* a, tc_stream_t stream) 
   TC_REQUIRE(a->M >= 0 && a->ldx >= 3, TC_ERR_SHAPE, "tc_point_embed: bad M/ldx");
   if (a->M == 0) return TC_OK;
   PointEmbedParams p{a->x, a->ldx, a->M, a->C, a->logit_input, a->weight, a->bias, a->ln_gamma, a->ln_beta,
-                     a->ln_eps, a->out_f32, static_cast<__nv_bfloat16*>(a->out_bf16)};
+                     a->ln_eps, a->out_f32, static_cast<__nv_bfloat16*>(a->out_bf16), a->out16_dtype == TC_BF16X2 ? 1 : 0};
   const bool al = (!a->out_f32 || aligned16(a->out_f32)) && (!a->out_bf16 || aligned16(a->out_bf16));
   if (a->C == 256 && al) {
     const int ctas = (a->M + 7) / 8;

@@ -1,23 +1,31 @@
-// K3 tensor-core path: Y = epilogue(A[M,K] * W[N,K]^T) with bf16 operands, fp32 accumulation in TMEM.
+// K3 tensor-core path: Y = epilogue(A[M,K] * W[N,K]^T) on tcgen05, fp32 accumulation in TMEM.
 //
 // The GEMMs of this path are small (M = B*900 rows, N <= 1536, K <= 512): one 128 x 64 output tile per CTA keeps
-// all 148 SMs busy (2-3 resident CTAs each) and makes the per-thread epilogue short.
-//   * operands: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a 4-stage shared-memory ring (24 KB per stage),
-//     full/empty mbarriers; both operands are K-major (nn.Linear keeps W as [N,K]).
+// all 148 SMs busy (2 resident CTAs each) and makes the per-thread epilogue short.
+//   * operands: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a shared-memory ring, full/empty mbarriers; both
+//     operands are K-major (nn.Linear keeps W as [N,K]).
 //   * math: tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x 64 x 16, issued by one thread; accumulator = 128 lanes x
-//     64 fp32 columns of tensor memory.
-//   * the input-side epilogue terms (bias, per-query row bias, residuals) do not depend on the product, so the four
-//     epilogue warps load them WHILE the operands are in flight, write their sum into the accumulator's tensor
-//     memory (tcgen05.st) and the MMAs then accumulate on top of it: no side-input latency after the last MMA.
+//     64 fp32 columns of tensor memory.  Two operand modes:
+//       TC_BF16    one pass over bf16 operands (4-stage ring, 24 KB per stage);
+//       TC_BF16X2  "bf16x3": both operands arrive split (hi | lo halves of a [rows, 2K] bf16 matrix, tc_cast_split / the
+//                  split epilogue below); per K block the ring stage holds A_hi, A_lo, W_hi, W_lo (48 KB, 2 stages) and
+//                  the issuer runs hi*hi, lo*hi, hi*lo into the same accumulator: ~16 mantissa bits per operand, results
+//                  within ~1e-5 of the fp32 reference for 3x the (otherwise idle) tensor-pipe work.
+//   * the input-side epilogue terms (bias, per-query row bias, residuals) do not depend on the product: the four
+//     epilogue warps request them while the operands are in flight, keep them in registers and add them after the
+//     accumulator is complete (folding them into the accumulator BEFORE the MMAs made the MMAs wait for those loads).
 //   * output side: one accumulator row per thread (tcgen05.ld 32x32b): LayerNorm / ReLU / post-add, 256-bit row
-//     stores.  LayerNorm needs the whole row (N = 64, 128 or 256): the 1, 2 or 4 CTAs that share a row block form
-//     a thread-block cluster and exchange per-row (sum, sum of squares) through distributed shared memory.
+//     stores; fp32 and / or a 16-bit copy (bf16, split bf16 for the next bf16x3 GEMM, or fp16 for the attention core).
+//     LayerNorm needs the whole row (N = 64, 128 or 256): the 1, 2 or 4 CTAs that share a row block form a
+//     thread-block cluster and exchange per-row (sum, sum of squares) through distributed shared memory.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
 #include <cuda.h>
 
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
+
+#include <cuda_fp16.h>
 
 #include "tc_common.cuh"
 #include "tc_sm100.cuh"
@@ -28,18 +36,24 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 64;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int kStages = 4;
 constexpr int kThreads = 192;
 constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kBBytes = BN * BK * 2;
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
-// after the ring: barriers (full, empty, acc, init) + tmem slot, column vectors (bias, gamma, beta), LN partials
-constexpr uint32_t kOffBars = kStages * kStageBytes;
-constexpr uint32_t kOffVec = kOffBars + 128;
-constexpr uint32_t kOffPart = kOffVec + 3 * BN * 4;
 constexpr int kMaxCluster = 4;                        // LayerNorm rows span at most 4 CTAs (N <= 256)
-constexpr uint32_t kSmemUsed = kOffPart + kMaxCluster * BM * 8;
-constexpr size_t kSmemBytes = kSmemUsed + 1024;          // + alignment slack
+// shared-memory carve-up per operand mode.  after the ring: barriers (full, empty, acc, init) + tmem slot, column
+// vectors (bias, gamma, beta), LN partials
+// kDeep: the 4-stage ring of the split mode (192 KB: one CTA per SM) for grids of at most one CTA per SM, where nothing
+// is gained by leaving room for a second CTA and a 2-stage ring serialises the K loop (N <= 64: 57 CTAs at M = 7200).
+template <bool kSplit, bool kDeep = false>
+struct Cfg {
+  static constexpr int kStages = (kSplit && !kDeep) ? 2 : 4;
+  static constexpr uint32_t kStageBytes = (kSplit ? 2u : 1u) * (kABytes + kBBytes);   // split: A_hi, A_lo, W_hi, W_lo
+  static constexpr uint32_t kOffBars = kStages * kStageBytes;
+  static constexpr uint32_t kOffVec = kOffBars + 128;
+  static constexpr uint32_t kOffPart = kOffVec + 3 * BN * 4;
+  static constexpr uint32_t kSmemUsed = kOffPart + kMaxCluster * BM * 8;
+  static constexpr size_t kSmemBytes = kSmemUsed + 1024;          // + alignment slack
+};
 
 struct EpiParams {
   int M, N, K;
@@ -53,6 +67,7 @@ struct EpiParams {
   const float* post_add; long long ld_post_add;
   float* out_f32; long long ld_out_f32;
   __nv_bfloat16* out_bf16; long long ld_out_bf16;
+  int out16;      // TC_BF16, TC_BF16X2 (hi at column n, lo at column N + n) or TC_F16
   int vec;        // 1: every row-wise operand is 32-byte aligned with a 32-byte multiple pitch -> 256-bit accesses
   int has_init;   // bias / row_bias / residual(s) are folded into the accumulator before the first MMA
 };
@@ -88,6 +103,13 @@ __device__ __forceinline__ void add_row32(const float* row, int ncols, bool vec,
   }
 }
 
+__device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {       // saturating: +-65504 instead of inf
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -118,9 +140,12 @@ __device__ __forceinline__ unsigned long long ld_smem_u64(uint32_t addr) {
   return v;
 }
 
-template <bool kLN>
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool kLN, bool kSplit, bool kDeep>
+__global__ void __launch_bounds__(kThreads, kDeep ? 1 : 2)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const EpiParams p) {
+  using C = Cfg<kSplit, kDeep>;
+  constexpr int kStages = C::kStages;
+  constexpr uint32_t kStageBytes = C::kStageBytes, kOffBars = C::kOffBars, kOffVec = C::kOffVec, kOffPart = C::kOffPart;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // pointer arithmetic (not an integer round-trip) so the compiler keeps the shared address space: LDS/STS, not LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -164,8 +189,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, kStageBytes);
         const uint32_t a_dst = smem_base + s * kStageBytes;
-        tma_load_2d(a_dst, &map_a, kb * BK, m0, full0 + 8 * s);
-        tma_load_2d(a_dst + kABytes, &map_w, kb * BK, n0, full0 + 8 * s);
+        if (kSplit) {            // stage = A_hi | A_lo | W_hi | W_lo; the lo halves start at column K of the [rows, 2K] matrices
+          tma_load_2d(a_dst, &map_a, kb * BK, m0, full0 + 8 * s);
+          tma_load_2d(a_dst + 2 * kABytes, &map_w, kb * BK, n0, full0 + 8 * s);
+          tma_load_2d(a_dst + kABytes, &map_a, p.K + kb * BK, m0, full0 + 8 * s);
+          tma_load_2d(a_dst + 2 * kABytes + kBBytes, &map_w, p.K + kb * BK, n0, full0 + 8 * s);
+        } else {
+          tma_load_2d(a_dst, &map_a, kb * BK, m0, full0 + 8 * s);
+          tma_load_2d(a_dst + kABytes, &map_w, kb * BK, n0, full0 + 8 * s);
+        }
       }
     }
     __syncwarp();
@@ -187,10 +219,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
         const uint32_t a_addr = smem_base + s * kStageBytes;
-        const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + kABytes);
+        if (kSplit) {                              // hi*hi, then the two cross terms, into the same accumulator
+          const uint64_t dah = make_desc_sw128(a_addr), dal = make_desc_sw128(a_addr + kABytes);
+          const uint64_t dwh = make_desc_sw128(a_addr + 2 * kABytes), dwl = make_desc_sw128(a_addr + 2 * kABytes + kBBytes);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)          // +32 bytes (2 x 16 B) per UMMA_K step inside the 128 B row
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, ((int)init_in_tmem | kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_base, dah + 2 * k, dwh + 2 * k, idesc, ((int)init_in_tmem | kb | k) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, dal + 2 * k, dwh + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, dah + 2 * k, dwl + 2 * k, idesc, 1u);
+        } else {
+          const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)          // +32 bytes (2 x 16 B) per UMMA_K step inside the 128 B row
+            umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, ((int)init_in_tmem | kb | k) ? 1u : 0u);
+        }
         umma_commit(empty0 + 8 * s);               // frees the smem slot once these MMAs retire
       }
       umma_commit(accbar);                         // accumulator complete
@@ -312,18 +356,38 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         if (p.out_bf16) {
           uint32_t u[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) u[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
           __nv_bfloat16* dst = p.out_bf16 + (long long)m * p.ld_out_bf16 + n;
+          if (p.out16 == TC_F16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = pack_f16_sat(v[2 * i], v[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+          }
           st256u(dst, u);
           st256u(dst + 16, u + 8);
+          if (p.out16 == TC_BF16X2) {            // lo = bf16(v - hi) at column N + n
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = pack_bf16(v[2 * i] - bf16_lo(u[i]), v[2 * i + 1] - bf16_hi(u[i]));
+            st256u(dst + p.N, u);
+            st256u(dst + p.N + 16, u + 8);
+          }
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (j < nc) {
             if (p.out_f32) p.out_f32[(long long)m * p.ld_out_f32 + n + j] = v[j];
-            if (p.out_bf16) p.out_bf16[(long long)m * p.ld_out_bf16 + n + j] = __float2bfloat16_rn(v[j]);
+            if (p.out_bf16) {
+              __nv_bfloat16* d16 = p.out_bf16 + (long long)m * p.ld_out_bf16 + n + j;
+              if (p.out16 == TC_F16) {
+                *reinterpret_cast<__half*>(d16) = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+              } else {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+                *d16 = hi;
+                if (p.out16 == TC_BF16X2) d16[p.N] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+              }
+            }
           }
         }
       }
@@ -457,20 +521,22 @@ bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CU
   return true;
 }
 
-template <bool kLN>
+template <bool kLN, bool kSplit, bool kDeep = false>
 int launch_tile(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
   CUtensorMap ma, mw;
-  if (!get_map(a->A, a->lda, a->M, a->K, BM, &ma)) return TC_ERR_SHAPE;
-  if (!get_map(a->W, a->ldw, a->N, a->K, BN, &mw)) return TC_ERR_SHAPE;
+  const int kcols = kSplit ? 2 * a->K : a->K;       // split operands: [rows, 2K] = hi | lo
+  constexpr size_t kSmemBytes = Cfg<kSplit, kDeep>::kSmemBytes;
+  if (!get_map(a->A, a->lda, a->M, kcols, BM, &ma)) return TC_ERR_SHAPE;
+  if (!get_map(a->W, a->ldw, a->N, kcols, BN, &mw)) return TC_ERR_SHAPE;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<kLN, kSplit, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { set_error("tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
   const unsigned ntiles = (unsigned)((a->N + BN - 1) / BN);
   // LayerNorm: the CTAs of one row block form a cluster and exchange row statistics
-  cudaError_t e = launch(linear_tc_kernel<kLN>, dim3(ntiles, (unsigned)((a->M + BM - 1) / BM)), dim3(kThreads), kSmemBytes, s,
+  cudaError_t e = launch(linear_tc_kernel<kLN, kSplit, kDeep>, dim3(ntiles, (unsigned)((a->M + BM - 1) / BM)), dim3(kThreads), kSmemBytes, s,
                          kLN ? ntiles : 1u, ma, mw, ep);
   if (e != cudaSuccess) { set_error("tc_linear(tcgen05): %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   count_launch();
@@ -482,11 +548,6 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 }  // namespace
 
-// shared with chain_tc.cu: cached K-major SWIZZLE_128B tensor map, box = [64 cols, box_rows rows]
-bool tensor_map_bf16_2d(const void* ptr, long long ld, int rows, int cols, int box_rows, CUtensorMap* out) {
-  return get_map(ptr, ld, rows, cols, box_rows, out);
-}
-
 // 256-bit row accesses: every row-wise operand 32-byte aligned, pitch a multiple of 32 bytes
 static bool epilogue_vectorizable(const tc_linear_args* a) {
   if (a->row_bias && (!al32(a->row_bias) || a->ld_row_bias % 8 != 0)) return false;
@@ -495,14 +556,17 @@ static bool epilogue_vectorizable(const tc_linear_args* a) {
   if (a->post_add && (!al32(a->post_add) || a->ld_post_add % 8 != 0)) return false;
   if (a->out_f32 && (!al32(a->out_f32) || a->ld_out_f32 % 8 != 0)) return false;
   if (a->out_bf16 && (!al32(a->out_bf16) || a->ld_out_bf16 % 16 != 0)) return false;
+  if (a->out_bf16 && a->out16_dtype == TC_BF16X2 && a->N % 16 != 0) return false;      // lo half starts at column N
   return true;
 }
 
 bool linear_tc_supported(const tc_linear_args* a) {
   static const bool disabled = getenv("TC_DISABLE_TC_LINEAR") != nullptr;        // debugging / A-B measurements
   if (disabled) return false;
-  if (a->a_dtype != TC_BF16 || a->w_dtype != TC_BF16) return false;
+  const bool split = a->a_dtype == TC_BF16X2 && a->w_dtype == TC_BF16X2;
+  if (!split && (a->a_dtype != TC_BF16 || a->w_dtype != TC_BF16)) return false;
   if (a->K % 8 != 0 || a->K < BK) return false;       // 16-byte row pitch; a partial last K block is zero-filled
+  if (split && a->K % BK != 0) return false;          // ... which the hi | lo layout does not allow
   // fused LayerNorm: the row block's CTAs form one cluster (portable size <= 8) -> N = 64, 128 or 256 here
   if (a->ln_gamma && !(a->N == 64 || a->N == 128 || a->N == 256)) return false;
   // TMA: 16-byte aligned base and row pitch for both operands
@@ -524,9 +588,22 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   ep.post_add = a->post_add; ep.ld_post_add = a->ld_post_add;
   ep.out_f32 = a->out_f32; ep.ld_out_f32 = a->ld_out_f32;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); ep.ld_out_bf16 = a->ld_out_bf16;
+  ep.out16 = a->out16_dtype == 0 ? TC_BF16 : a->out16_dtype;
   ep.vec = epilogue_vectorizable(a) ? 1 : 0;
   ep.has_init = (a->row_bias || a->residual || a->residual2) ? 1 : 0;
-  return a->ln_gamma ? launch_tile<true>(a, ep, s) : launch_tile<false>(a, ep, s);
+  if (a->a_dtype == TC_BF16X2) {
+    static int sm_count = 0;
+    if (sm_count == 0) {
+      int dev = 0, n = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+      sm_count = n;
+    }
+    const long long ctas = (long long)((a->N + BN - 1) / BN) * ((a->M + BM - 1) / BM);
+    if (ctas <= sm_count && a->K > 2 * BK)        // at most one CTA per SM anyway: take the deep ring
+      return a->ln_gamma ? launch_tile<true, true, true>(a, ep, s) : launch_tile<false, true, true>(a, ep, s);
+    return a->ln_gamma ? launch_tile<true, true>(a, ep, s) : launch_tile<false, true>(a, ep, s);
+  }
+  return a->ln_gamma ? launch_tile<true, false>(a, ep, s) : launch_tile<false, false>(a, ep, s);
 }
 
 }  // namespace tc

@@ -46,6 +46,17 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, long long ld_src
   dst[(long long)r * ld_dst + c] = __float2bfloat16_rn(src[(long long)r * ld_src + c]);
 }
 
+__global__ void cast_split_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
+                                  long long ld_dst, int rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  const float v = src[(long long)r * ld_src + c];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  dst[(long long)r * ld_dst + c] = hi;
+  dst[(long long)r * ld_dst + cols + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
 // ---- N1 decode: one block per sample, bitonic sort of (score, index) keys in shared memory ----------
 // key = orderable(score) << 32 | ~index  ->  descending sort gives scores high-to-low, ties by low index.
 __device__ __forceinline__ uint32_t orderable(float f) {
@@ -55,7 +66,7 @@ __device__ __forceinline__ uint32_t orderable(float f) {
 
 struct DecodeParams {
   const float* cls; const float* code; int Q, classes, max_num, npad; float rng[6];
-  float* boxes; float* scores; int* labels; uint8_t* keep;
+  float* boxes; float* scores; int* labels; uint8_t* keep; float* records;
 };
 
 __global__ void __launch_bounds__(1024) decode_kernel(const DecodeParams p) {
@@ -83,26 +94,34 @@ __global__ void __launch_bounds__(1024) decode_kernel(const DecodeParams p) {
   }
   for (int r = threadIdx.x; r < p.max_num; r += blockDim.x) {
     const long long o = (long long)b * p.max_num + r;
-    float* bx = p.boxes + o * 9;
-    if (r >= n) {
-      for (int j = 0; j < 9; ++j) bx[j] = 0.f;
-      p.scores[o] = 0.f; p.labels[o] = 0; p.keep[o] = 0;
-      continue;
+    float bx[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float score = 0.f;
+    int label = 0;
+    bool in = false;
+    if (r < n) {
+      const unsigned long long k = keys[r];
+      const uint32_t idx = 0xffffffffu - (uint32_t)(k & 0xffffffffull);
+      const int qi = idx / p.classes;
+      const float* c = p.code + ((long long)b * p.Q + qi) * 10;
+      // U:26-52 denormalize: (cx,cy,w,l,cz,h,sin,cos,vx,vy) -> (cx,cy,cz,w,l,h,rot,vx,vy)
+      const float cx = c[0], cy = c[1], cz = c[4];
+      bx[0] = cx; bx[1] = cy; bx[2] = cz;
+      bx[3] = expf(c[2]); bx[4] = expf(c[3]); bx[5] = expf(c[5]);
+      bx[6] = atan2f(c[6], c[7]);
+      bx[7] = c[8]; bx[8] = c[9];
+      score = sigmoid_f32(cls[idx]);
+      label = (int)(idx % p.classes);
+      in = cx >= p.rng[0] && cy >= p.rng[1] && cz >= p.rng[2] && cx <= p.rng[3] && cy <= p.rng[4] && cz <= p.rng[5];
     }
-    const unsigned long long k = keys[r];
-    const uint32_t idx = 0xffffffffu - (uint32_t)(k & 0xffffffffull);
-    const int qi = idx / p.classes;
-    const float* c = p.code + ((long long)b * p.Q + qi) * 10;
-    // U:26-52 denormalize: (cx,cy,w,l,cz,h,sin,cos,vx,vy) -> (cx,cy,cz,w,l,h,rot,vx,vy)
-    const float cx = c[0], cy = c[1], cz = c[4];
-    bx[0] = cx; bx[1] = cy; bx[2] = cz;
-    bx[3] = expf(c[2]); bx[4] = expf(c[3]); bx[5] = expf(c[5]);
-    bx[6] = atan2f(c[6], c[7]);
-    bx[7] = c[8]; bx[8] = c[9];
-    p.scores[o] = sigmoid_f32(cls[idx]);
-    p.labels[o] = (int)(idx % p.classes);
-    const bool in = cx >= p.rng[0] && cy >= p.rng[1] && cz >= p.rng[2] && cx <= p.rng[3] && cy <= p.rng[4] && cz <= p.rng[5];
-    p.keep[o] = in ? 1 : 0;
+    if (p.boxes) {
+      for (int j = 0; j < 9; ++j) p.boxes[o * 9 + j] = bx[j];
+      p.scores[o] = score; p.labels[o] = label; p.keep[o] = in ? 1 : 0;
+    }
+    if (p.records) {
+      float* rec = p.records + o * 12;
+      for (int j = 0; j < 9; ++j) rec[j] = bx[j];
+      rec[9] = score; rec[10] = (float)label; rec[11] = in ? 1.f : 0.f;
+    }
   }
 }
 
@@ -150,6 +169,19 @@ extern "C" int tc_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t
   return check_launch("tc_cast_bf16");
 }
 
+extern "C" int tc_cast_split(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
+                             tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(src && dst, TC_ERR_NULL, "tc_cast_split: NULL pointer");
+  TC_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= 2 * (int64_t)cols, TC_ERR_SHAPE, "tc_cast_split: bad shape");
+  const long long n = (long long)rows * cols;
+  if (n == 0) return TC_OK;
+  cast_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols);
+  count_launch();
+  return check_launch("tc_cast_split");
+}
+
 extern "C" int64_t tc_decode_workspace_bytes(int32_t B, int32_t Q, int32_t classes) {
   (void)B; (void)Q; (void)classes;
   return 0;   // the sort runs in shared memory
@@ -158,13 +190,17 @@ extern "C" int64_t tc_decode_workspace_bytes(int32_t B, int32_t Q, int32_t class
 extern "C" int tc_decode(const tc_decode_args* a, tc_stream_t stream) {
   using namespace tc;
   TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_decode: args is NULL");
-  TC_REQUIRE(a->cls && a->code && a->boxes && a->scores && a->labels && a->keep, TC_ERR_NULL, "tc_decode: NULL pointer");
+  TC_REQUIRE(a->cls && a->code, TC_ERR_NULL, "tc_decode: NULL input pointer");
+  const bool quad = a->boxes && a->scores && a->labels && a->keep;
+  TC_REQUIRE(quad || (!a->boxes && !a->scores && !a->labels && !a->keep), TC_ERR_NULL,
+             "tc_decode: boxes / scores / labels / keep go together");
+  TC_REQUIRE(quad || a->records, TC_ERR_NULL, "tc_decode: no output pointer");
   TC_REQUIRE(a->B >= 0 && a->Q > 0 && a->classes > 0 && a->max_num > 0, TC_ERR_SHAPE, "tc_decode: bad shape");
   const int n = a->Q * a->classes;
   const int npad = next_pow2(n);
   TC_REQUIRE((size_t)npad * 8 <= 200 * 1024, TC_ERR_SHAPE, "tc_decode: Q*classes = %d too large for the in-smem sort", n);
   if (a->B == 0) return TC_OK;
-  DecodeParams p{a->cls, a->code, a->Q, a->classes, a->max_num, npad, {}, a->boxes, a->scores, a->labels, a->keep};
+  DecodeParams p{a->cls, a->code, a->Q, a->classes, a->max_num, npad, {}, a->boxes, a->scores, a->labels, a->keep, a->records};
   for (int i = 0; i < 6; ++i) p.rng[i] = a->post_center_range[i];
   const size_t smem = (size_t)npad * 8;
   cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

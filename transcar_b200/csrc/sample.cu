@@ -53,6 +53,7 @@ struct SampleParams {
   float inv_q;             // 1.0f / Q
   void* out;
   uint8_t* mask;
+  int all_cams;            // TC_SAMPLE_ALL_CAMS
 };
 
 // ATen grid_sampler_unnormalize, align_corners=False: ((g + 1) * size - 1) / 2.
@@ -99,8 +100,11 @@ __device__ __forceinline__ void fetch_query(const SampleParams& p, int task, int
   }
 }
 
-template <bool kBf16In, bool kBf16Out, int kWarps, int kSlots>
+// kOut: 0 = fp32 [.., C], 1 = bf16 [.., C], 2 = split bf16 [.., 2C] (hi | lo: the A operand of a bf16x3 Linear)
+template <bool kBf16In, int kOut, int kWarps, int kSlots>
 __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SampleParams p) {
+  constexpr bool kBf16Out = kOut != 0;
+  constexpr int kOutRow = kOut == 2 ? 2 : 1;           // output row pitch in units of C
   constexpr int kPer = kBf16In ? 8 : 4;                 // channels per lane per chunk (16 bytes)
   constexpr int kChunkCh = kBf16In ? 256 : 128;         // channels per 512-byte chunk
   constexpr int kRingBytes = kWarps * kSlots * kSlotBytes;
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SamplePara
       }
     }
     if (mt.z & 2) {
-      const size_t o = (size_t)mt.x * p.C + mt.y + lane * kPer;
+      const size_t o = (size_t)mt.x * p.C * kOutRow + mt.y + lane * kPer;
       if (kBf16Out) {
         __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + o;
         if (kBf16In) {
@@ -161,10 +165,22 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SamplePara
           u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
           u.z = pack_bf16(acc[4 % kPer], acc[5 % kPer]); u.w = pack_bf16(acc[6 % kPer], acc[7 % kPer]);
           *reinterpret_cast<uint4*>(dst) = u;
+          if (kOut == 2) {
+            uint4 l;
+            l.x = pack_bf16(acc[0] - bf16_lo(u.x), acc[1] - bf16_hi(u.x)); l.y = pack_bf16(acc[2] - bf16_lo(u.y), acc[3] - bf16_hi(u.y));
+            l.z = pack_bf16(acc[4 % kPer] - bf16_lo(u.z), acc[5 % kPer] - bf16_hi(u.z));
+            l.w = pack_bf16(acc[6 % kPer] - bf16_lo(u.w), acc[7 % kPer] - bf16_hi(u.w));
+            *reinterpret_cast<uint4*>(dst + p.C) = l;
+          }
         } else {
           uint2 u;
           u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
           *reinterpret_cast<uint2*>(dst) = u;
+          if (kOut == 2) {
+            uint2 l;
+            l.x = pack_bf16(acc[0] - bf16_lo(u.x), acc[1] - bf16_hi(u.x)); l.y = pack_bf16(acc[2] - bf16_lo(u.y), acc[3] - bf16_hi(u.y));
+            *reinterpret_cast<uint2*>(dst + p.C) = l;
+          }
         }
       } else {
         float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
@@ -227,7 +243,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SamplePara
       valid = valid && (gx > -1.0f) && (gx < 1.0f) && (gy > -1.0f) && (gy < 1.0f);
       if (p.mask) p.mask[(size_t)task * p.N + lane] = valid ? 1 : 0;
     }
-    const unsigned vset = __ballot_sync(0xffffffffu, valid);
+    const unsigned vset = __ballot_sync(0xffffffffu, valid || (p.all_cams && lane < p.N));
 
     // -- sigmoid(attention logits): lane i < N*4 holds weight i = cam*4 + level ----------------------
     const float wgt = (lane < p.N * 4) ? sigmoid_f32(cur.logit) : 0.f;
@@ -236,8 +252,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SamplePara
     if (next < range_end) fetch_query(p, next, lane, nxt);
 
     if (vset == 0) {                                    // no camera sees the point: the masked sum is exactly 0
-      for (int c = lane * kPer; c < p.C; c += 32 * kPer) {
-        const size_t o = (size_t)task * p.C + c;
+      for (int c = lane * kPer; c < p.C * kOutRow; c += 32 * kPer) {
+        const size_t o = (size_t)task * p.C * kOutRow + c;
         if (kBf16Out) {
           if (kPer == 8) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o) = make_uint4(0, 0, 0, 0);
           else *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + o) = make_uint2(0, 0);
@@ -330,11 +346,11 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
-template <bool kBf16In, bool kBf16Out, int kWarps, int kSlots>
+template <bool kBf16In, int kOut, int kWarps, int kSlots>
 cudaError_t launch_sample(const SampleParams& p, long long total, int sm_count, cudaStream_t s) {
   constexpr int smem = sample_smem(kWarps, kSlots);
   static bool configured = false;
-  auto kernel = sample_kernel<kBf16In, kBf16Out, kWarps, kSlots>;
+  auto kernel = sample_kernel<kBf16In, kOut, kWarps, kSlots>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -370,7 +386,8 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   TC_REQUIRE(a->B >= 0 && a->Q >= 0 && (long long)a->B * a->Q < (1ll << 22), TC_ERR_SHAPE, "tc_sample_fwd: bad B/Q (B * Q must be < 2^22)");
   TC_REQUIRE(aligned16(a->lidar2img), TC_ERR_ALIGN, "tc_sample_fwd: lidar2img must be 16-byte aligned");
   TC_REQUIRE(a->feat_dtype == TC_F32 || a->feat_dtype == TC_BF16, TC_ERR_DTYPE, "tc_sample_fwd: bad feat dtype");
-  TC_REQUIRE(a->out_dtype == TC_F32 || a->out_dtype == TC_BF16, TC_ERR_DTYPE, "tc_sample_fwd: bad out dtype");
+  TC_REQUIRE(a->out_dtype == TC_F32 || a->out_dtype == TC_BF16 || a->out_dtype == TC_BF16X2, TC_ERR_DTYPE,
+             "tc_sample_fwd: bad out dtype");
   TC_REQUIRE(aligned16(a->out), TC_ERR_ALIGN, "tc_sample_fwd: out must be 16-byte aligned");
   if (a->B == 0 || a->Q == 0) return TC_OK;
   SampleParams p;
@@ -385,6 +402,7 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   for (int i = 0; i < 6; ++i) p.pc[i] = a->pc_range[i];
   p.inv_w = 1.0f / a->img_w; p.inv_h = 1.0f / a->img_h; p.inv_q = 1.0f / (float)a->Q;
   p.out = a->out; p.mask = a->mask;
+  p.all_cams = (a->flags & TC_SAMPLE_ALL_CAMS) ? 1 : 0;
   // persistent warps, one CTA per SM; each CTA hands its range of queries out to its warps dynamically
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -394,18 +412,20 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
     sm_count = n;
   }
   cudaStream_t s = as_stream(stream);
-  const bool bi = a->feat_dtype == TC_BF16, bo = a->out_dtype == TC_BF16;
+  const bool bi = a->feat_dtype == TC_BF16, bo = a->out_dtype == TC_BF16, so = a->out_dtype == TC_BF16X2;
   const long long total = (long long)a->B * a->Q;
   cudaError_t e = cudaSuccess;
   // bf16 in / bf16 out (the engine's path): 24 warps x 1 slot is faster back to back (10.5 us vs 10.9 us for 12 x 2,
   // tools/k1_bench.py: the launch ramp hides behind the previous launch) but slower inside the step (bracket 19.8 us vs
   // 18.4 us, step +9 us: 768-thread CTAs start later), so 12 x 2 stays the default.
   if (bi && bo) {
-    if (sample_variant() == 1) e = launch_sample<true, true, 24, 1>(p, total, sm_count, s);
-    else e = launch_sample<true, true, 12, 2>(p, total, sm_count, s);
-  } else if (bi) e = launch_sample<true, false, 12, 2>(p, total, sm_count, s);
-  else if (bo) e = launch_sample<false, true, 12, 2>(p, total, sm_count, s);
-  else e = launch_sample<false, false, 12, 2>(p, total, sm_count, s);
+    if (sample_variant() == 1) e = launch_sample<true, 1, 24, 1>(p, total, sm_count, s);
+    else e = launch_sample<true, 1, 12, 2>(p, total, sm_count, s);
+  } else if (bi && so) e = launch_sample<true, 2, 12, 2>(p, total, sm_count, s);
+  else if (bi) e = launch_sample<true, 0, 12, 2>(p, total, sm_count, s);
+  else if (so) e = launch_sample<false, 2, 12, 2>(p, total, sm_count, s);
+  else if (bo) e = launch_sample<false, 1, 12, 2>(p, total, sm_count, s);
+  else e = launch_sample<false, 0, 12, 2>(p, total, sm_count, s);
   if (e != cudaSuccess) { set_error("tc_sample_fwd: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   count_launch();
   return check_launch("tc_sample_fwd");

@@ -12,8 +12,12 @@ What changes w.r.t. the reference dataflow (results stay within the stated toler
     ``reg_branches[5](hs[5])`` at H:284 equals the decoder's own refinement regression (T:191) and is reused.
   * the radar block runs batched (the reference is batch-1 only, SURVEY F4) with per-sample radar tokens;
     the [Q,R] mask never exists in memory and there is no ``torch.where`` host sync (H:573).
-Precision: ``fp32`` (CUDA-core path, parity mode) or ``bf16`` (tensor-core path: bf16 operands, fp32
-accumulation, fp32 residual stream / LayerNorm / reference points / masks).
+Precision modes (fp32 residual stream / LayerNorm / reference points / masks / accumulation in all of them):
+  * ``bf16x3`` (default) - tensor cores at parity grade: every GEMM operand is a split-bf16 pair (hi | lo, 16 mantissa
+    bits) and every product is hi*hi + lo*hi + hi*lo on tcgen05; the dense self-attention runs on fp16 q/k/v/P (11
+    bits), the sparse radar attention on fp32 q/k/v.  End to end within 1e-3 abs / 1e-2 rel of the fp32 reference.
+  * ``bf16`` - one tensor-core pass over bf16 operands: fastest, ~1e-2 end-to-end deviations after 9 chained layers.
+  * ``fp32`` - CUDA-core path, bit-level parity mode (1e-5 per stage).
 """
 from __future__ import annotations
 
@@ -28,17 +32,19 @@ RADIUS_CLAMP = ((1.0, 2.0), (1.0, 2.0), (0.5, 1.0))      # H:567, H:635, H:693
 
 class FusionDecoderEngine:
     def __init__(self, state_dict, *, num_query, embed_dims=256, num_heads=8, num_layers=6, num_cams=6,
-                 num_levels=4, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), precision="bf16",
+                 num_levels=4, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), precision="bf16x3",
                  device="cuda"):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "bf16x3"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x3'")
         self.Q, self.C, self.heads, self.L = num_query, embed_dims, num_heads, num_layers
         self.N, self.levels = num_cams, num_levels
         self.pc_range = [float(x) for x in pc_range]
         self.precision = precision
-        self.bf16 = precision == "bf16"
+        self.bf16 = precision in ("bf16", "bf16x3")      # tensor-core modes
+        self.x3 = precision == "bf16x3"
+        self.out16 = "split" if self.x3 else "bf16"      # 16-bit format of activations that feed the next GEMM
         self.device = torch.device(device)
-        self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
+        self.act_dtype = "split" if self.x3 else (torch.bfloat16 if self.bf16 else torch.float32)
         self.sample_events = None        # set to a list to collect (start, end) CUDA events per K1 launch
         self.external_events = False     # True while capturing: events become graph nodes (timing inside a graph)
         self.keep_cam_masks = False      # set True to collect the [B,Q,N] validity mask of every layer
@@ -49,6 +55,7 @@ class FusionDecoderEngine:
         self._keep = []                  # tensors that cross streams stay referenced until the forward ends
         self._graphs = {}
         self._init_cache = {}
+        self._pinned = {}                # host staging buffers (pinned once, reused every forward)
         self._prepare(state_dict)
 
     # ------------------------------------------------------------------ weights
@@ -60,25 +67,19 @@ class FusionDecoderEngine:
         self.w = {}
         for k, v in f32.items():
             if v.dim() == 2 and (k.endswith("weight") or k.endswith("in_proj_weight")) and "embedding" not in k:
-                self.w[k] = ops.cast_bf16(v) if self.bf16 else v
+                self.w[k] = self._cast_w(v)
         C = self.C
-        emb = f32["query_embedding.weight"]
-        self.query_pos = emb[:, :C].contiguous()          # T:119
-        self.query = emb[:, C:].contiguous()
-        # T:122-123  reference_points = sigmoid(Linear(query_pos)); input independent
-        r, _ = ops.linear(self.query_pos, f32["transformer.reference_points.weight"],
-                          f32["transformer.reference_points.bias"])
-        self.init_ref = torch.sigmoid(r).contiguous()     # [Q,3]
+        self.query = self.query_pos = self.init_ref = None
         self.row_bias_qkv, self.row_bias_aw = [], []
-        for l in range(self.L):
-            p = f"transformer.decoder.layers.{l}."
-            w_in, b_in = f32[p + "attentions.0.attn.in_proj_weight"], f32[p + "attentions.0.attn.in_proj_bias"]
-            qk, _ = ops.linear(self.query_pos, w_in[:2 * C], b_in[:2 * C])           # [Q,2C] fp32 exact path
-            rb = torch.cat([qk, b_in[2 * C:].unsqueeze(0).expand(self.Q, -1)], dim=1).contiguous()
-            self.row_bias_qkv.append(rb)
-            aw, _ = ops.linear(self.query_pos, f32[p + "attentions.1.attention_weights.weight"],
-                               f32[p + "attentions.1.attention_weights.bias"])
-            self.row_bias_aw.append(aw.contiguous())
+        if "query_embedding.weight" in f32:               # absent: decoder-only engine driven with caller-given queries
+            emb = f32["query_embedding.weight"]
+            self.query_pos = emb[:, :C].contiguous()      # T:119
+            self.query = emb[:, C:].contiguous()
+            # T:122-123  reference_points = sigmoid(Linear(query_pos)); input independent
+            r, _ = ops.linear(self.query_pos, f32["transformer.reference_points.weight"],
+                              f32["transformer.reference_points.bias"])
+            self.init_ref = torch.sigmoid(r).contiguous() # [Q,3]
+            self.row_bias_qkv, self.row_bias_aw = self._row_biases(self.query_pos)
         self.has_radar = "rf_multihead_attn.in_proj_weight" in f32
         if not self.has_radar:       # decoder-only use (Detr3DTransformer called on its own)
             torch.cuda.current_stream().synchronize()
@@ -86,12 +87,33 @@ class FusionDecoderEngine:
         # radar K/V projections of the three layers stacked: [3*2C, C]
         names = ("rf_multihead_attn", "rf_multihead_attn2", "rf_multihead_attn3")
         wkv = torch.cat([f32[n + ".in_proj_weight"][C:] for n in names], 0).contiguous()
-        self.radar_wkv = ops.cast_bf16(wkv) if self.bf16 else wkv
+        self.radar_wkv = self._cast_w(wkv)
         self.radar_bkv = torch.cat([f32[n + ".in_proj_bias"][C:] for n in names], 0).contiguous()
-        self.radar_wq = [(ops.cast_bf16(f32[n + ".in_proj_weight"][:C].contiguous()) if self.bf16
-                          else f32[n + ".in_proj_weight"][:C].contiguous()) for n in names]
+        self.radar_wq = [self._cast_w(f32[n + ".in_proj_weight"][:C].contiguous()) for n in names]
         self.radar_bq = [f32[n + ".in_proj_bias"][:C].contiguous() for n in names]
         torch.cuda.current_stream().synchronize()
+
+    def _row_biases(self, query_pos):
+        """Input-independent terms of the projections that see ``x + query_pos``: ``query_pos W^T + b`` for the q / k
+        rows of the self-attention in-projection (the v rows see x only: bias alone) and for the 24 sampling logits
+        (T:355-362).  fp32 exact path; one [rows, 3C] and one [rows, 24] matrix per layer."""
+        C, f32 = self.C, self.f32
+        rb_qkv, rb_aw = [], []
+        for l in range(self.L):
+            p = f"transformer.decoder.layers.{l}."
+            w_in, b_in = f32[p + "attentions.0.attn.in_proj_weight"], f32[p + "attentions.0.attn.in_proj_bias"]
+            qk, _ = ops.linear(query_pos, w_in[:2 * C], b_in[:2 * C])
+            rb_qkv.append(torch.cat([qk, b_in[2 * C:].unsqueeze(0).expand(query_pos.shape[0], -1)], dim=1).contiguous())
+            aw, _ = ops.linear(query_pos, f32[p + "attentions.1.attention_weights.weight"],
+                               f32[p + "attentions.1.attention_weights.bias"])
+            rb_aw.append(aw.contiguous())
+        return rb_qkv, rb_aw
+
+    def _cast_w(self, v):
+        """GEMM operand copy of an fp32 matrix in the engine's compute format (library cast kernels)."""
+        if self.x3:
+            return ops.cast_split(v)
+        return ops.cast_bf16(v) if self.bf16 else v
 
     # ------------------------------------------------------------------ parallel branches
     # Several sub-chains of the step do not depend on each other: the position encoder of a decoder layer needs only the
@@ -139,7 +161,7 @@ class FusionDecoderEngine:
         w = self.w[key + ".weight"]
         b = self.f32[key + ".bias"] if bias else None
         if self.bf16 and (feed or both):
-            o32, o16 = ops.linear(x, w, b, want_f32=both, want_bf16=True, **kw)
+            o32, o16 = ops.linear(x, w, b, want_f32=both, want_bf16=True, out16=self.out16, **kw)
             return (o32, o16) if both else o16
         o32, _ = ops.linear(x, w, b, **kw)
         return (o32, o32) if both else o32
@@ -148,24 +170,55 @@ class FusionDecoderEngine:
         return (self.f32[key + ".weight"], self.f32[key + ".bias"])
 
     def _prep_feats(self, mlvl_feats):
-        want = torch.bfloat16 if self.bf16 else torch.float32
+        """Feature hand-off: channels-last maps are taken zero-copy (bf16 in the tensor-core modes, fp32 in the fp32 and
+        bf16x3 modes); NCHW fp32 maps are re-laid out by ``tc_nchw_to_nhwc`` (to bf16 only in the one-pass bf16 mode -
+        the parity-grade modes keep the values they were given)."""
+        if self.x3:
+            ok = (torch.bfloat16, torch.float32)
+        else:
+            ok = (torch.bfloat16,) if self.bf16 else (torch.float32,)
         out = []
         for f in mlvl_feats:
-            if f.dtype != want and ops.is_channels_last_5d(f):
-                raise RuntimeError(f"transcar_b200: engine precision {self.precision} needs {want} channels-last "
-                                   f"features (got {f.dtype}); hand over NCHW fp32 or cast upstream")
-            out.append(ops.to_channels_last(f, want))
+            if ops.is_channels_last_5d(f):
+                if f.dtype not in ok:
+                    raise RuntimeError(f"transcar_b200: engine precision {self.precision} needs channels-last features in "
+                                       f"{ok} (got {f.dtype}); hand over NCHW fp32 or cast upstream")
+                out.append(f)
+            else:
+                out.append(ops.to_channels_last(f, torch.bfloat16 if (self.bf16 and not self.x3) else torch.float32))
+        if len({f.dtype for f in out}) != 1:
+            raise RuntimeError("transcar_b200: feature levels disagree in dtype")
         return out
 
+    def _staging(self, name, shape):
+        """Pinned host buffer for one small per-frame input, allocated once per (name, shape).  The previous upload from it
+        is awaited before the host overwrites it."""
+        key = (name, tuple(shape))
+        ent = self._pinned.get(key)
+        if ent is None:
+            ent = self._pinned[key] = [torch.empty(shape, dtype=torch.float32).pin_memory(), None]
+        if ent[1] is not None:
+            ent[1].synchronize()
+        return ent
+
+    def _upload(self, ent):
+        dev = ent[0].to(self.device, non_blocking=True)
+        ent[1] = torch.cuda.Event()
+        ent[1].record()
+        return dev
+
     def _prep_metas(self, img_metas, B):
-        l2i = np.asarray([m["lidar2img"] for m in img_metas], dtype=np.float64).astype(np.float32)   # T:384-386
-        l2i = torch.from_numpy(l2i).pin_memory().to(self.device, non_blocking=True).reshape(B, self.N, 4, 4)
+        ent = self._staging("l2i", (B, self.N, 4, 4))
+        ent[0].numpy()[...] = np.asarray([m["lidar2img"] for m in img_metas], dtype=np.float64).reshape(B, self.N, 4, 4)  # T:384-386
+        l2i = self._upload(ent)
         shape0 = img_metas[0]["img_shape"][0]
         return l2i, float(shape0[1]), float(shape0[0])
 
     def _prep_radar(self, img_metas, B):
         R = MAX_RADAR_TOKENS
-        host = np.full((B, R, NUM_RADAR_FEATS), RADAR_PAD_VALUE, dtype=np.float32)       # H:526-530
+        ent, ent_xy = self._staging("tokens", (B, R, NUM_RADAR_FEATS)), self._staging("key_xy", (B, R, 2))
+        host = ent[0].numpy()
+        host[...] = RADAR_PAD_VALUE                                                        # H:526-530
         for b, m in enumerate(img_metas):
             if "radar_tokens" not in m:
                 raise KeyError("img_metas[%d] lacks 'radar_tokens' ([n,36] float32); the forward pass is I/O free - "
@@ -173,14 +226,27 @@ class FusionDecoderEngine:
             t = np.asarray(m["radar_tokens"], dtype=np.float32).reshape(-1, NUM_RADAR_FEATS)
             n = min(R, t.shape[0])
             host[b, :n] = t[:n]
-        tok = torch.from_numpy(host).pin_memory().to(self.device, non_blocking=True)
-        key_xy = torch.from_numpy(np.ascontiguousarray(host[:, :, :2])).pin_memory().to(self.device, non_blocking=True)
-        return tok, key_xy
+        ent_xy[0].numpy()[...] = host[:, :, :2]
+        return self._upload(ent), self._upload(ent_xy)
 
     # ------------------------------------------------------------------ decoder (a2-a7)
-    def decoder(self, feats, l2i, img_w, img_h, B, keep_all=True):
+    def decoder(self, feats, l2i, img_w, img_h, B, keep_all=True, defer_join=False, init=None, refine=True):
+        """6 decoder layers.  Returns (hs, refs, x32, x16, ref, code) with every tensor safe to read on the current stream,
+        unless ``defer_join`` (only ``_forward_eager``: ``radar_layers`` then joins the last refinement itself, after it
+        has queued the first radar query projection).
+        ``init = (query [B*Q,C], reference_points [B*Q,3], query_pos [B*Q,C])`` starts the loop from caller-given state
+        (the reference's ``Detr3DTransformerDecoder.forward`` signature, T:155-160) instead of the learned embedding;
+        ``refine=False`` leaves the reference points untouched (``reg_branches is None``, T:190)."""
         Q, C, M = self.Q, self.C, B * self.Q
-        x32, x16, ref = self._initial_state(B)
+        if init is None:
+            x32, x16, ref = self._initial_state(B)
+            rb_qkv, rb_aw, period = self.row_bias_qkv, self.row_bias_aw, Q
+        else:
+            x32, ref, query_pos = init
+            x16 = self._cast_w(x32)
+            rb_qkv, rb_aw = self._row_biases(query_pos)
+            period = M
+            self._keep.extend((x32, x16, ref, query_pos, *rb_qkv, *rb_aw))
         hs, refs = [], []
         code = None
         pos_feat = None
@@ -190,14 +256,15 @@ class FusionDecoderEngine:
                 with self._branch(0):
                     pos_feat = self._position_encoder(p, ref)
             # --- self attention (mmcv MultiheadAttention wrapper around nn.MultiheadAttention)
-            qkv = self._in_proj(x16, p + "attentions.0.attn", self.row_bias_qkv[l])
+            qkv = self._in_proj(x16, p + "attentions.0.attn", rb_qkv[l], period)
             qkv3 = qkv.view(B, Q, 3 * C)
-            att, _ = ops.attention(qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], self.heads)
+            att, _ = ops.attention(qkv3[:, :, :C], qkv3[:, :, C:2 * C], qkv3[:, :, 2 * C:], self.heads,
+                                   out_dtype="split" if self.x3 else None)
             x32, x16 = self._lin(att.view(M, C), p + "attentions.0.attn.out_proj", both=True,
                                  residual=x32, ln=self._ln(p + "norms.0"))
             # --- Detr3DCrossAtten (T:302-378)
             aw = self._lin(x16, p + "attentions.1.attention_weights", bias=False,
-                           row_bias=self.row_bias_aw[l], row_bias_period=Q)
+                           row_bias=rb_aw[l], row_bias_period=period)
             # join here, between the logits and the sampling launch: before the logits (+37 us per step) or after the
             # sampling launch (+37 us) were both measured slower
             self._join(0, pos_feat, ref)     # reference points refined by the previous layer + their position feature
@@ -223,19 +290,19 @@ class FusionDecoderEngine:
             # --- branch: iterative refinement (T:190-203) and the next layer's position encoder (T:377).  The next
             # layer's self-attention needs only x, so this chain (~45 us) hides behind in_proj + attention + out_proj.
             with self._branch(0):
-                r = self._lin(x16, f"reg_branches.{l}.0", feed=True, relu=True)
-                r2 = self._lin(r, f"reg_branches.{l}.2", feed=True, relu=True)
-                code = self._lin(r2, f"reg_branches.{l}.4")
-                ref = ops.ref_update(code, ref)
-                self._keep.extend((x16, r, r2, code, ref))
+                if refine:
+                    r = self._lin(x16, f"reg_branches.{l}.0", feed=True, relu=True)
+                    r2 = self._lin(r, f"reg_branches.{l}.2", feed=True, relu=True)
+                    code = self._lin(r2, f"reg_branches.{l}.4")
+                    ref = ops.ref_update(code, ref)
+                    self._keep.extend((x16, r, r2, code, ref))
                 if l + 1 < self.L:
                     pos_feat = self._position_encoder(f"transformer.decoder.layers.{l + 1}.", ref)
             if keep_all or l == self.L - 1:
                 hs.append(x32)
                 refs.append(ref)
-        if keep_all or not self.has_radar:
+        if not defer_join:
             self._join(0, ref, code)
-        # otherwise radar_layers joins the last refinement itself, after it has queued the first query projection
         return hs, refs, x32, x16, ref, code
 
     def _position_encoder(self, p, ref):
@@ -243,7 +310,7 @@ class FusionDecoderEngine:
         pe, pe16 = ops.point_embed(ref, self.f32[p + "attentions.1.position_encoder.0.weight"],
                                    self.f32[p + "attentions.1.position_encoder.0.bias"],
                                    *self._ln(p + "attentions.1.position_encoder.1"), logit_input=True,
-                                   want_f32=not self.bf16, want_bf16=self.bf16)
+                                   want_f32=not self.bf16, want_bf16=self.bf16, out16=self.out16)
         pos_feat = self._lin(pe16 if self.bf16 else pe, p + "attentions.1.position_encoder.3",
                              ln=self._ln(p + "attentions.1.position_encoder.4"), relu=True)
         self._keep.extend((pe, pe16, ref))
@@ -256,15 +323,16 @@ class FusionDecoderEngine:
         if st is None:
             Q, C = self.Q, self.C
             x32 = self.query.unsqueeze(0).expand(B, Q, C).reshape(B * Q, C).contiguous()
-            x16 = ops.cast_bf16(x32) if self.bf16 else x32
+            x16 = self._cast_w(x32)
             ref = self.init_ref.unsqueeze(0).expand(B, Q, 3).reshape(B * Q, 3).contiguous()
             st = self._init_cache[B] = (x32, x16, ref)
         return st
 
-    def _in_proj(self, x16, prefix, row_bias):
+    def _in_proj(self, x16, prefix, row_bias, period):
         w = self.w[prefix + ".in_proj_weight"]
-        o32, o16 = ops.linear(x16, w, None, row_bias=row_bias, row_bias_period=self.Q,
-                              want_f32=not self.bf16, want_bf16=self.bf16)
+        # q / k / v feed the attention core only: bf16 (one-pass mode) or fp16 (bf16x3 mode: 11 mantissa bits)
+        o32, o16 = ops.linear(x16, w, None, row_bias=row_bias, row_bias_period=period,
+                              want_f32=not self.bf16, want_bf16=self.bf16, out16="f16" if self.x3 else "bf16")
         return o16 if self.bf16 else o32
 
     # ------------------------------------------------------------------ radar fusion (a10-a14)
@@ -273,13 +341,13 @@ class FusionDecoderEngine:
         t2 = tokens.view(B * R, NUM_RADAR_FEATS)
         pe32, pe16 = ops.point_embed(t2, self.f32["radar_position_encoder.0.weight"],
                                      self.f32["radar_position_encoder.0.bias"], *self._ln("radar_position_encoder.1"),
-                                     logit_input=False, want_f32=not self.bf16, want_bf16=self.bf16)
+                                     logit_input=False, want_f32=not self.bf16, want_bf16=self.bf16, out16=self.out16)
         pos = self._lin(pe16 if self.bf16 else pe32, "radar_position_encoder.3",
                         ln=self._ln("radar_position_encoder.4"), relu=True)                  # fp32 [BR,C]
         # first feature layer stays fp32 x fp32 in both modes: raw radar fields (metres, ids, the 500 pad)
         # would lose up to 0.25 m to bf16 rounding
         f32o, f16o = ops.linear(t2, self.f32["radar_feat_encoder.0.weight"], self.f32["radar_feat_encoder.0.bias"],
-                                relu=True, want_f32=not self.bf16, want_bf16=self.bf16)
+                                relu=True, want_f32=not self.bf16, want_bf16=self.bf16, out16=self.out16)
         f = f16o if self.bf16 else f32o
         f = self._lin(f, "radar_feat_encoder.2", feed=True, relu=True)
         kv = self._lin(f, "radar_feat_encoder.4", feed=True, relu=True, post_add=pos)      # H:536
@@ -290,9 +358,11 @@ class FusionDecoderEngine:
         tokens only, so the whole chain runs beside the decoder."""
         R = tokens.shape[1]
         kvfeat = self.radar_encode(tokens, B)                                               # [BR,C]
-        o32, o16 = ops.linear(kvfeat, self.radar_wkv, self.radar_bkv, want_f32=not self.bf16, want_bf16=self.bf16)
+        # K / V of the sparse radar attention: bf16 in the one-pass mode, fp32 otherwise (the kernel touches ~0.1 % of them)
+        one_pass = self.bf16 and not self.x3
+        o32, o16 = ops.linear(kvfeat, self.radar_wkv, self.radar_bkv, want_f32=not one_pass, want_bf16=one_pass)
         self._keep.append(kvfeat)
-        return (o16 if self.bf16 else o32).view(B, R, 6 * self.C)
+        return (o16 if one_pass else o32).view(B, R, 6 * self.C)
 
     def _start_radar_branch(self):
         """Radar encoders + K/V projections on side stream 1.  Started right after the sampling launch of the
@@ -307,15 +377,20 @@ class FusionDecoderEngine:
 
     def radar_layers(self, x32, x16, ref, code, KV, key_xy, B):
         Q, C, M = self.Q, self.C, B * self.Q
-        cls_all = torch.empty((3, B, Q, 10), device=self.device, dtype=torch.float32)
-        reg_all = torch.empty((3, B, Q, 10), device=self.device, dtype=torch.float32)
+        n_cls = self.f32["final_cls.6.weight"].shape[0]            # cls_out_channels (10 in the TransCAR configs)
+        n_code = self.f32["final_reg.4.weight"].shape[0]           # code_size: the radar geometry / anchor columns need 10
+        if n_code != 10:
+            raise RuntimeError(f"transcar_b200: code_size must be 10 (got {n_code}): H:543-567 / H:596-600 index columns 0-7")
+        cls_all = torch.empty((3, B, Q, n_cls), device=self.device, dtype=torch.float32)
+        reg_all = torch.empty((3, B, Q, n_code), device=self.device, dtype=torch.float32)
         anchor, centre_norm = ref, True
         aux = {}
 
         def q_proj(li, x16):       # needs only x: queued before / beside the regression head that feeds the geometry
-            q32, q16 = ops.linear(x16, self.radar_wq[li], self.radar_bq[li], want_f32=not self.bf16, want_bf16=self.bf16)
+            one_pass = self.bf16 and not self.x3
+            q32, q16 = ops.linear(x16, self.radar_wq[li], self.radar_bq[li], want_f32=not one_pass, want_bf16=one_pass)
             self._keep.extend((x16, q32, q16))
-            return (q16 if self.bf16 else q32).view(B, Q, C)
+            return (q16 if one_pass else q32).view(B, Q, C)
 
         qp = q_proj(0, x16)
         self._join(0, ref, code)                 # last decoder refinement (side branch)
@@ -328,7 +403,8 @@ class FusionDecoderEngine:
                 self._join(1, qp)
             att, row_any = ops.attention(qp, KV[:, :, (2 * li) * C:(2 * li + 1) * C],
                                          KV[:, :, (2 * li + 1) * C:(2 * li + 2) * C], self.heads,
-                                         geom=geom, key_xy=key_xy, want_row_any=True)
+                                         geom=geom, key_xy=key_xy, want_row_any=True,
+                                         out_dtype="split" if self.x3 else None)
             x32, x16 = self._lin(att.view(M, C), "rf_multihead_attn" + m + ".out_proj", both=True,
                                  row_gate=row_any.view(M), residual=x32, ln=self._ln("rf_norm2" + s))
             h = self._lin(x16, "rf_linear1" + s, feed=True, relu=True)
@@ -340,11 +416,11 @@ class FusionDecoderEngine:
                 c = self._lin(x16, "final_cls" + m + ".0", feed=True, ln=self._ln("final_cls" + m + ".1"), relu=True)
                 c2 = self._lin(c, "final_cls" + m + ".3", feed=True, ln=self._ln("final_cls" + m + ".4"), relu=True)
                 ops.linear(c2, self.w["final_cls" + m + ".6.weight"], self.f32["final_cls" + m + ".6.bias"],
-                           out_f32=cls_all[li].view(M, 10))
+                           out_f32=cls_all[li].view(M, n_cls))
                 self._keep.extend((c, c2, x16))
             g = self._lin(x16, "final_reg" + m + ".0", feed=True, relu=True)
             g = self._lin(g, "final_reg" + m + ".2", feed=True, relu=True)
-            reg = reg_all[li].view(M, 10)
+            reg = reg_all[li].view(M, n_code)
             ops.linear(g, self.w["final_reg" + m + ".4.weight"], self.f32["final_reg" + m + ".4.bias"], out_f32=reg)
             if li == 0:   # H:596-600: x,y of the refined reference in metres, z left normalised (quirk Q3)
                 ops.box_anchor_add(reg, anchor, 0, 2, True, self.pc_range)
@@ -359,7 +435,7 @@ class FusionDecoderEngine:
         return cls_all, reg_all, aux
 
     # ------------------------------------------------------------------ whole head (a8)
-    def prepare_inputs(self, mlvl_feats, img_metas):
+    def prepare_inputs(self, mlvl_feats, img_metas, radar=None):
         """Host -> device staging of one batch: feature layout/dtype hand-off, lidar2img (float64 -> fp32,
         T:384-386), padded radar tokens (H:526-530).  Returns the tuple ``forward_prepared`` consumes."""
         B = mlvl_feats[0].shape[0]
@@ -369,7 +445,8 @@ class FusionDecoderEngine:
             mlvl_feats = [f.to(self.device, non_blocking=True) for f in mlvl_feats]
         feats = self._prep_feats(mlvl_feats)
         l2i, img_w, img_h = self._prep_metas(img_metas, B)
-        tokens, key_xy = self._prep_radar(img_metas, B) if self.has_radar else (None, None)
+        radar = self.has_radar if radar is None else radar
+        tokens, key_xy = self._prep_radar(img_metas, B) if radar else (None, None)
         return feats, l2i, img_w, img_h, tokens, key_xy
 
     def _forward_eager(self, prepared, return_aux=False):
@@ -378,7 +455,14 @@ class FusionDecoderEngine:
         self._keep = []
         self._radar_job = (tokens, B) if self.has_radar else None
         self._radar_kv = None
-        hs, refs, x32, x16, ref, code = self.decoder(feats, l2i, img_w, img_h, B, keep_all=return_aux)
+        if return_aux:
+            self.keep_cam_masks, self.cam_masks = True, []
+        try:
+            hs, refs, x32, x16, ref, code = self.decoder(feats, l2i, img_w, img_h, B, keep_all=return_aux,
+                                                         defer_join=self.has_radar)
+        finally:
+            if return_aux:
+                self.keep_cam_masks = False
         self._start_radar_branch()                 # no-op when the decoder already started it
         KV = self._radar_kv
         self._join(1, KV)
@@ -388,6 +472,8 @@ class FusionDecoderEngine:
         if return_aux:
             aux["hs"] = hs
             aux["refs"] = refs
+            aux["cam_masks"], self.cam_masks = self.cam_masks, []        # per layer [B,Q,N] uint8 (T:400-409)
+            aux["key_xy"] = key_xy
             out["aux"] = aux
         return out
 

@@ -11,9 +11,49 @@ import math
 import torch
 
 from . import _lib
-from ._lib import TC_BF16, TC_F32
+from ._lib import TC_BF16, TC_BF16X2, TC_F16, TC_F32
 
-_DT = {torch.float32: TC_F32, torch.bfloat16: TC_BF16}
+_DT = {torch.float32: TC_F32, torch.bfloat16: TC_BF16, torch.float16: TC_F16}
+
+
+class SplitBf16:
+    """Split-bf16 matrix (``TC_BF16X2``): logical ``[..., cols]`` stored as bf16 ``[..., 2 * cols]`` = ``hi | lo`` with
+    ``hi = bf16(x)``, ``lo = bf16(x - hi)``.  The operand format of the bf16x3 tensor-core mode."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        assert t.dtype == torch.bfloat16 and t.shape[-1] % 2 == 0
+        self.t = t
+
+    @property
+    def shape(self):
+        return (*self.t.shape[:-1], self.t.shape[-1] // 2)
+
+    @property
+    def device(self):
+        return self.t.device
+
+    def view(self, *shape):
+        """View with the LOGICAL trailing dimension, e.g. ``[B,Q,C] -> view(B*Q, C)``."""
+        return SplitBf16(self.t.view(*shape[:-1], 2 * shape[-1]))
+
+    def float(self):
+        c = self.t.shape[-1] // 2
+        return self.t[..., :c].float() + self.t[..., c:].float()
+
+
+def _out16(kind, shape, device):
+    """Allocate the 16-bit output of a kernel: kind in {'bf16', 'split', 'f16'} -> (tensor, wrapped, dtype code)."""
+    if kind == "split":
+        t = torch.empty((*shape[:-1], 2 * shape[-1]), device=device, dtype=torch.bfloat16)
+        return t, SplitBf16(t), TC_BF16X2
+    if kind == "f16":
+        t = torch.empty(shape, device=device, dtype=torch.float16)
+        return t, t, TC_F16
+    if kind != "bf16":
+        raise ValueError(f"unknown 16-bit output kind {kind!r}")
+    t = torch.empty(shape, device=device, dtype=torch.bfloat16)
+    return t, t, TC_BF16
 
 # Profiling hook (tools/step_timeline.py): when set to a list, every library call is bracketed by a pair of CUDA
 # events (external=True, so the pair becomes two nodes of a captured CUDA graph) and (label, start, end) is appended.
@@ -83,8 +123,9 @@ def to_channels_last(f, dtype=None):
 
 
 def sample_fwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, out_dtype=torch.float32,
-               want_mask=False, out=None):
+               want_mask=False, out=None, all_cams=False):
     """feats: 4 x logical [B,N,C,H,W] channels-last; ref [B,Q,3]; lidar2img [B,N,4,4]; attn_logits [B,Q,N*L].
+    ``out_dtype``: torch.float32 / torch.bfloat16 / ``"split"`` (SplitBf16 [B,Q,C]).
     Returns (out [B,Q,C], mask [B,Q,N] uint8 or None)."""
     lib = _lib.load()
     a = _lib.SampleArgs()
@@ -104,36 +145,52 @@ def sample_fwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, out_d
     lidar2img = _need(lidar2img, "lidar2img", torch.float32).contiguous()
     attn_logits = _need(attn_logits, "attn_logits", torch.float32).contiguous()
     assert ref.shape == (B, Q, 3) and lidar2img.shape == (B, N, 4, 4) and attn_logits.shape == (B, Q, N * 4)
+    ret = out
     if out is None:
-        out = torch.empty((B, Q, Cc), device=ref.device, dtype=out_dtype)
+        if out_dtype == "split":
+            out, ret, _ = _out16("split", (B, Q, Cc), ref.device)
+        else:
+            ret = out = torch.empty((B, Q, Cc), device=ref.device, dtype=out_dtype)
+    elif isinstance(out, SplitBf16):
+        out = out.t
     mask = torch.empty((B, Q, N), device=ref.device, dtype=torch.uint8) if want_mask else None
     a.num_levels, a.B, a.N, a.Q, a.C = 4, B, N, Q, Cc
-    a.feat_dtype, a.out_dtype = _DT[feats[0].dtype], _DT[out.dtype]
+    a.feat_dtype = _DT[feats[0].dtype]
+    a.out_dtype = TC_BF16X2 if isinstance(ret, SplitBf16) else _DT[out.dtype]
     a.ref, a.lidar2img, a.attn_logits = ref.data_ptr(), lidar2img.data_ptr(), attn_logits.data_ptr()
     for i in range(6):
         a.pc_range[i] = float(pc_range[i])
     a.img_w, a.img_h = float(img_w), float(img_h)
     a.out = out.data_ptr()
     a.mask = mask.data_ptr() if mask is not None else None
+    a.flags = _lib.TC_SAMPLE_ALL_CAMS if all_cams else 0
     _lib.check(_call("sample", lib.tc_sample_fwd, C.byref(a), _stream()), "sample_fwd")
-    return out, mask
+    return ret, mask
 
 
 # --------------------------------------------------------------------------------------- K3
 def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, residual=None, residual2=None,
            ln=None, ln_eps=1e-5, relu=False, post_add=None, out_f32=None, out_bf16=None,
-           want_f32=True, want_bf16=False):
-    """Y = epilogue(A @ W^T) - see ``tc_linear`` in include/transcar_b200.h.  A [M,K], W [N,K].
-    ``ln`` = (gamma, beta).  Returns (out_f32 or None, out_bf16 or None)."""
+           want_f32=True, want_bf16=False, out16="bf16"):
+    """Y = epilogue(A @ W^T) - see ``tc_linear`` in include/transcar_b200.h.  A [M,K], W [N,K]; both fp32, both bf16
+    or both :class:`SplitBf16` (bf16x3).  ``ln`` = (gamma, beta).  ``out16`` = format of the 16-bit output when
+    ``want_bf16``: 'bf16', 'split' (SplitBf16) or 'f16'.  Returns (out_f32 or None, 16-bit output or None)."""
     lib = _lib.load()
+    split = isinstance(A, SplitBf16)
+    if split != isinstance(W, SplitBf16):
+        raise RuntimeError("transcar_b200.linear: split-bf16 operands come in pairs (A and W)")
+    if split:
+        A, W = A.t, W.t
     A, lda = _rows(_need(A, "A"), "A")
     W, ldw = _rows(_need(W, "W"), "W")
     M, K = A.shape
     N = W.shape[0]
     assert W.shape[1] == K, (A.shape, W.shape)
+    if split:
+        K //= 2
     a = _lib.LinearArgs()
-    a.A, a.a_dtype, a.lda = A.data_ptr(), _DT[A.dtype], lda
-    a.W, a.w_dtype, a.ldw = W.data_ptr(), _DT[W.dtype], ldw
+    a.A, a.a_dtype, a.lda = A.data_ptr(), TC_BF16X2 if split else _DT[A.dtype], lda
+    a.W, a.w_dtype, a.ldw = W.data_ptr(), TC_BF16X2 if split else _DT[W.dtype], ldw
     a.M, a.N, a.K = M, N, K
     keep = [A, W]
     if bias is not None:
@@ -164,119 +221,36 @@ def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, 
         keep.append(pa)
     if out_f32 is None and want_f32:
         out_f32 = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    ret16 = out_bf16
     if out_bf16 is None and want_bf16:
-        out_bf16 = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
+        out_bf16, ret16, a.out16_dtype = _out16(out16, (M, N), A.device)
+    elif out_bf16 is not None:
+        if isinstance(out_bf16, SplitBf16):
+            out_bf16, a.out16_dtype = out_bf16.t, TC_BF16X2
+        else:
+            a.out16_dtype = _DT[out_bf16.dtype]
     if out_f32 is not None:
         o, ldo = _rows(_need(out_f32, "out_f32", torch.float32), "out_f32")
+        if o.shape != (M, N):
+            raise RuntimeError(f"transcar_b200.linear: out_f32 has shape {tuple(o.shape)}, expected {(M, N)}")
         a.out_f32, a.ld_out_f32 = o.data_ptr(), ldo
     if out_bf16 is not None:
-        o, ldo = _rows(_need(out_bf16, "out_bf16", torch.bfloat16), "out_bf16")
+        o, ldo = _rows(_need(out_bf16, "out16"), "out16")
+        if o.shape != (M, 2 * N if a.out16_dtype == TC_BF16X2 else N):
+            raise RuntimeError(f"transcar_b200.linear: 16-bit output has shape {tuple(o.shape)} for M, N = {(M, N)}")
         a.out_bf16, a.ld_out_bf16 = o.data_ptr(), ldo
     label = "linear" if TIMELINE is None else (
-        f"linear M{M} N{N} K{K} {'bf16' if A.dtype == torch.bfloat16 else 'f32'}" + ("+rb" if row_bias is not None else "") +
+        f"linear M{M} N{N} K{K} {'bf16x3' if split else 'bf16' if A.dtype == torch.bfloat16 else 'f32'}" + ("+rb" if row_bias is not None else "") +
         ("+gate" if row_gate is not None else "") + ("+res" if residual is not None else "") +
         ("+res2" if residual2 is not None else "") + ("+ln" if ln is not None else "") + ("+relu" if relu else "") +
         ("+post" if post_add is not None else ""))
     _lib.check(_call(label, lib.tc_linear, C.byref(a), _stream()), "linear")
-    return out_f32, out_bf16
+    return out_f32, ret16
 
 
-_CHAIN_EPI = {"none": _lib.TC_CHAIN_NONE, "act": _lib.TC_CHAIN_ACT, "ln": _lib.TC_CHAIN_LN, "out": _lib.TC_CHAIN_OUT}
-
-
-def chain_stage(W, *, a_buf=0, acc_col=0, accumulate=False, epi="act", relu=False, dst_buf=-1, keep_col=-1,
-                init_bias=None, residual=None, residual2=None, row_gate=None, bias=None, ln=None, ln_eps=1e-5,
-                fold_bias=None, row_bias=None, row_bias_period=0, out_f32=None, out_f32_add=None,
-                out_bf16=None, ref_update=None, anchor_add=None):
-    """One stage of ``linear_chain`` (see ``tc_linear_chain`` in include/transcar_b200.h).  ``W`` is a bf16 [N,K] view.
-    ``ref_update=(ref_in [M,3], ref_out [M,3])``; ``anchor_add=(anchor [M,ld], xy_col, z_col, from_norm, pc_range)``."""
-    return dict(W=W, a_buf=a_buf, acc_col=acc_col, accumulate=accumulate, epi=epi, relu=relu, dst_buf=dst_buf,
-                keep_col=keep_col, init_bias=init_bias, residual=residual, residual2=residual2, row_gate=row_gate,
-                bias=bias, ln=ln, ln_eps=ln_eps, fold_bias=fold_bias, row_bias=row_bias,
-                row_bias_period=row_bias_period, out_f32=out_f32, out_f32_add=out_f32_add, out_bf16=out_bf16,
-                ref_update=ref_update,
-                anchor_add=anchor_add)
-
-
-def linear_chain(A, stages, label="chain"):
-    """Row-local chain of Linear layers in one launch: A [M,K] bf16, ``stages`` = list of ``chain_stage(...)`` dicts.
-    Outputs are the tensors named by the stages (``out_f32`` / ``out_bf16`` / ``ref_update[1]``)."""
-    lib = _lib.load()
-    A, lda = _rows(_need(A, "A", torch.bfloat16), "A")
-    a = _lib.ChainArgs()
-    a.A, a.lda, a.M, a.K, a.num_stages = A.data_ptr(), lda, A.shape[0], A.shape[1], len(stages)
-    if len(stages) > _lib.TC_CHAIN_MAX_STAGES:
-        raise RuntimeError(f"transcar_b200.linear_chain: at most {_lib.TC_CHAIN_MAX_STAGES} stages")
-    keep = [A]
-    M = A.shape[0]
-
-    def f32rows(t, name):
-        t2, ld = _rows(_need(t, name, torch.float32), name)
-        assert t2.shape[0] == M, (name, t2.shape, M)
-        keep.append(t2)
-        return t2.data_ptr(), ld
-
-    def f32vec(t, name):
-        _need(t, name, torch.float32)
-        keep.append(t)
-        return t.data_ptr()
-
-    for i, sd in enumerate(stages):
-        st = a.stage[i]
-        W, ldw = _rows(_need(sd["W"], "W", torch.bfloat16), "W")
-        keep.append(W)
-        st.W, st.ldw, st.N, st.K = W.data_ptr(), ldw, W.shape[0], W.shape[1]
-        st.a_buf, st.acc_col, st.accumulate = sd["a_buf"], sd["acc_col"], 1 if sd["accumulate"] else 0
-        st.epi, st.relu = _CHAIN_EPI[sd["epi"]], 1 if sd["relu"] else 0
-        st.dst_buf, st.keep_col = sd["dst_buf"], sd["keep_col"]
-        st.init = 1 if (sd["init_bias"] is not None or sd["residual"] is not None or sd["residual2"] is not None) else 0
-        if sd["init_bias"] is not None:
-            st.init_bias = f32vec(sd["init_bias"], "init_bias")
-        if sd["residual"] is not None:
-            st.residual, st.ld_residual = f32rows(sd["residual"], "residual")
-        if sd["residual2"] is not None:
-            st.residual2, st.ld_residual2 = f32rows(sd["residual2"], "residual2")
-        if sd["row_gate"] is not None:
-            st.row_gate = _need(sd["row_gate"], "row_gate", torch.uint8).data_ptr()
-        if sd["bias"] is not None:
-            st.bias = f32vec(sd["bias"], "bias")
-        if sd["ln"] is not None:
-            st.ln_gamma, st.ln_beta = f32vec(sd["ln"][0], "ln_gamma"), f32vec(sd["ln"][1], "ln_beta")
-        st.ln_eps = float(sd["ln_eps"])
-        if sd["fold_bias"] is not None:
-            st.fold_bias = f32vec(sd["fold_bias"], "fold_bias")
-        if sd["row_bias"] is not None:
-            rb, ldrb = _rows(_need(sd["row_bias"], "row_bias", torch.float32), "row_bias")
-            keep.append(rb)
-            st.row_bias, st.ld_row_bias, st.row_bias_period = rb.data_ptr(), ldrb, sd["row_bias_period"] or rb.shape[0]
-        if sd["out_f32"] is not None:
-            st.out_f32, st.ld_out_f32 = f32rows(sd["out_f32"], "out_f32")
-        if sd["out_f32_add"] is not None:
-            st.out_f32_add, st.ld_out_f32_add = f32rows(sd["out_f32_add"], "out_f32_add")
-        if sd["out_bf16"] is not None:
-            o, ldo = _rows(_need(sd["out_bf16"], "out_bf16", torch.bfloat16), "out_bf16")
-            keep.append(o)
-            st.out_bf16, st.ld_out_bf16 = o.data_ptr(), ldo
-        if sd["ref_update"] is not None:
-            rin, rout = sd["ref_update"]
-            st.tail = _lib.TC_CHAIN_TAIL_REF_UPDATE
-            st.tail_in, st.ld_tail_in = f32rows(rin, "ref_in")
-            if not rout.is_contiguous() or rout.shape[-1] != 3:
-                raise RuntimeError("transcar_b200.linear_chain: ref_out must be contiguous [M,3]")
-            st.tail_out = _need(rout, "ref_out", torch.float32).data_ptr()
-        elif sd["anchor_add"] is not None:
-            anchor, xy_col, z_col, from_norm, pc_range = sd["anchor_add"]
-            st.tail = _lib.TC_CHAIN_TAIL_ANCHOR_ADD
-            st.tail_in, st.ld_tail_in = f32rows(anchor, "anchor")
-            st.tail_xy_col, st.tail_z_col, st.tail_from_norm = xy_col, z_col, 1 if from_norm else 0
-            for j in range(6):
-                st.pc_range[j] = float(pc_range[j])
-    lbl = label if TIMELINE is None else f"{label} M{M} x{len(stages)}"
-    _lib.check(_call(lbl, lib.tc_linear_chain, C.byref(a), _stream()), "linear_chain")
-
-
-def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, want_f32=True, want_bf16=False):
-    """ReLU(LN(Linear_{3->C}(f(x[:, :3])))); x [M, ldx>=3] fp32."""
+def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, want_f32=True, want_bf16=False,
+                out16="bf16"):
+    """ReLU(LN(Linear_{3->C}(f(x[:, :3])))); x [M, ldx>=3] fp32.  ``out16``: 'bf16' or 'split'."""
     lib = _lib.load()
     x, ldx = _rows(_need(x, "x", torch.float32), "x")
     M, Cc = x.shape[0], weight.shape[0]
@@ -288,10 +262,12 @@ def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, wa
     a.ln_beta = _need(ln_beta, "ln_beta", torch.float32).data_ptr()
     a.ln_eps = float(ln_eps)
     o32 = torch.empty((M, Cc), device=x.device, dtype=torch.float32) if want_f32 else None
-    o16 = torch.empty((M, Cc), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    o16 = r16 = None
+    if want_bf16:
+        o16, r16, a.out16_dtype = _out16(out16, (M, Cc), x.device)
     a.out_f32, a.out_bf16 = _ptr(o32), _ptr(o16)
     _lib.check(_call(f"point_embed M{M}", lib.tc_point_embed, C.byref(a), _stream()), "point_embed")
-    return o32, o16
+    return o32, r16
 
 
 # --------------------------------------------------------------------------------------- K4
@@ -300,7 +276,8 @@ ATTN_ALGOS = {"auto": _lib.TC_ATTN_AUTO, "tensor": _lib.TC_ATTN_TENSOR, "simt": 
 
 def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_row_any=False, scale=None, out=None,
               algo="auto"):
-    """q [B,Lq,E], k/v [B,Lk,E] (views with a row stride are fine) -> out [B,Lq,E], row_any [B,Lq] or None."""
+    """q [B,Lq,E], k/v [B,Lk,E] (fp32, bf16 or fp16; views with a row stride are fine) -> out [B,Lq,E], row_any [B,Lq]
+    or None.  ``out_dtype``: a torch dtype or ``"split"`` (SplitBf16)."""
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _need(t, n)
@@ -310,8 +287,14 @@ def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_ro
     Lk = k.shape[1]
     D = E // heads
     out_dtype = out_dtype or q.dtype
+    ret = out
     if out is None:
-        out = torch.empty((B, Lq, E), device=q.device, dtype=out_dtype)
+        if out_dtype == "split":
+            out, ret, _ = _out16("split", (B, Lq, E), q.device)
+        else:
+            ret = out = torch.empty((B, Lq, E), device=q.device, dtype=out_dtype)
+    elif isinstance(out, SplitBf16):
+        out = out.t
     a = _lib.AttentionArgs()
     a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     a.ldq, a.ldk, a.ldv = q.stride(1), k.stride(1), v.stride(1)
@@ -325,11 +308,12 @@ def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_ro
         assert geom.shape[-1] == 8 and geom.numel() == B * Lq * 8 and key_xy.numel() == B * Lk * 2
         a.geom, a.key_xy = geom.data_ptr(), key_xy.data_ptr()
     row_any = torch.empty((B, Lq), device=q.device, dtype=torch.uint8) if want_row_any else None
-    a.out, a.ldo, a.out_dtype = out.data_ptr(), out.stride(1), _DT[out.dtype]
+    a.out, a.ldo = out.data_ptr(), out.stride(1)
+    a.out_dtype = TC_BF16X2 if isinstance(ret, SplitBf16) else _DT[out.dtype]
     a.row_any = _ptr(row_any)
     a.algo = ATTN_ALGOS[algo]
     _lib.check(_call(f"attention Lq{Lq} Lk{Lk} {algo}{' masked' if geom is not None else ''}", lib.tc_attention_fwd, C.byref(a), _stream()), "attention")
-    return out, row_any
+    return ret, row_any
 
 
 def radar_geometry(centre, code, pc_range, r_lo, r_hi, centre_is_normalised):
@@ -396,13 +380,35 @@ def cast_bf16(src):
     return dst.view(src.shape)
 
 
-def decode(cls, code, max_num, post_center_range):
-    """cls [B,Q,classes], code [B,Q,10] fp32 -> boxes [B,max_num,9], scores, labels (int32), keep (uint8)."""
+def cast_split(src):
+    """fp32 [rows, cols] -> :class:`SplitBf16` (hi | lo)."""
+    lib = _lib.load()
+    s, lds = _rows(_need(src, "src", torch.float32), "src")
+    dst = torch.empty((s.shape[0], 2 * s.shape[1]), device=s.device, dtype=torch.bfloat16)
+    _lib.check(lib.tc_cast_split(_ptr(s), lds, _ptr(dst), dst.stride(0) if dst.shape[0] > 1 else dst.shape[1],
+                                 s.shape[0], s.shape[1], _stream()), "cast_split")
+    return SplitBf16(dst.view(*src.shape[:-1], 2 * src.shape[-1]))
+
+
+def decode(cls, code, max_num, post_center_range, records=False):
+    """cls [B,Q,classes], code [B,Q,10] fp32 -> boxes [B,max_num,9], scores, labels (int32), keep (uint8); with
+    ``records=True`` instead ONE tensor [B,max_num,12] = (box, score, label, keep) - the result-gather record."""
     lib = _lib.load()
     cls = _need(cls, "cls", torch.float32).contiguous()
     code = _need(code, "code", torch.float32).contiguous()
     B, Q, classes = cls.shape
+    if code.shape != (B, Q, 10):
+        raise RuntimeError(f"transcar_b200.decode: box codes must be [B, Q, 10] (got {tuple(code.shape)})")
     dev = cls.device
+    if records:
+        rec = torch.empty((B, max_num, 12), device=dev, dtype=torch.float32)
+        a = _lib.DecodeArgs()
+        a.cls, a.code, a.B, a.Q, a.classes, a.max_num = cls.data_ptr(), code.data_ptr(), B, Q, classes, max_num
+        for i in range(6):
+            a.post_center_range[i] = float(post_center_range[i])
+        a.records = rec.data_ptr()
+        _lib.check(_call("decode", lib.tc_decode, C.byref(a), _stream()), "decode")
+        return rec
     boxes = torch.empty((B, max_num, 9), device=dev, dtype=torch.float32)
     scores = torch.empty((B, max_num), device=dev, dtype=torch.float32)
     labels = torch.empty((B, max_num), device=dev, dtype=torch.int32)
@@ -412,7 +418,7 @@ def decode(cls, code, max_num, post_center_range):
     for i in range(6):
         a.post_center_range[i] = float(post_center_range[i])
     a.boxes, a.scores, a.labels, a.keep = boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), keep.data_ptr()
-    _lib.check(lib.tc_decode(C.byref(a), _stream()), "decode")
+    _lib.check(_call("decode", lib.tc_decode, C.byref(a), _stream()), "decode")
     return boxes, scores, labels, keep
 
 

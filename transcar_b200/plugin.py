@@ -232,8 +232,10 @@ class Detr3DCrossAtten(nn.Module):
 
 def feature_sampling(mlvl_feats, reference_points, pc_range, img_metas):
     """API-compatible ``feature_sampling`` (reference ``detr3d_transformer.py:381-422``) for callers that want the
-    un-reduced view: returns ``(reference_points_3d, sampled [B,C,Q,N,1,L], mask [B,1,Q,N,1,1])``.  One K1
-    launch per (camera, level) one-hot weighting; the fused path (``Detr3DCrossAtten``) never materialises this."""
+    un-reduced view: returns ``(reference_points_3d, sampled [B,C,Q,N,1,L], mask [B,1,Q,N,1,1])``; like the reference,
+    ``sampled`` is NOT multiplied by the mask (cameras that fail the validity test are sampled too,
+    ``TC_SAMPLE_ALL_CAMS``).  One K1 launch per (camera, level) one-hot weighting; the fused path
+    (``Detr3DCrossAtten``) never materialises this."""
     B, N, C = mlvl_feats[0].shape[:3]
     Q = reference_points.shape[1]
     L = len(mlvl_feats)
@@ -249,7 +251,7 @@ def feature_sampling(mlvl_feats, reference_points, pc_range, img_metas):
         for l in range(L):
             logits = torch.full((B, Q, N * L), float("-inf"), device=dev)
             logits[:, :, n * L + l] = big
-            s, mask = ops.sample_fwd(feats, ref, l2i, logits, pc_range, shape0[1], shape0[0], want_mask=True)
+            s, mask = ops.sample_fwd(feats, ref, l2i, logits, pc_range, shape0[1], shape0[0], want_mask=True, all_cams=True)
             sampled[:, :, :, n, 0, l] = s.permute(0, 2, 1)
     return reference_points.clone(), sampled, mask.bool().view(B, 1, Q, N, 1, 1)
 
@@ -268,9 +270,49 @@ class Detr3DTransformerDecoder(nn.Module):
                                     for _ in range(num_layers))
         self.embed_dims = self.layers[0].embed_dims
         self.pre_norm = False
+        self.precision = kwargs.pop("precision", "bf16x3")      # extra key (not in the reference): engine precision mode
+        self._engine, self._engine_key = None, None
 
     def forward(self, query, *args, reference_points=None, reg_branches=None, **kwargs):
-        raise RuntimeError("transcar_b200: call Detr3DTransformer / Detr3DHead; the 6-layer loop is fused in the engine")
+        """Reference signature (T:155-214): ``query [Q,B,C]``, ``args = (key, value)`` with ``value`` = the 4 feature
+        levels, ``kwargs``: ``query_pos [Q,B,C]``, ``img_metas``.  Runs the fused 6-layer loop from the GIVEN query /
+        reference points; returns ``(stack [L,Q,B,C], stack [L,B,Q,3])`` when ``return_intermediate`` else
+        ``(output [Q,B,C], reference_points [B,Q,3])``."""
+        _no_grad_required(self)
+        value = args[1] if len(args) > 1 else kwargs.get("value")
+        if value is None or "img_metas" not in kwargs:
+            raise ValueError("Detr3DTransformerDecoder.forward needs value (feature levels) and img_metas")
+        query_pos = kwargs.get("query_pos")
+        Q, B, C = query.shape
+        sd = {"transformer.decoder." + k: v for k, v in self.state_dict().items()}
+        if reg_branches is not None:
+            for i, br in enumerate(reg_branches):
+                for k, v in br.state_dict().items():
+                    sd[f"reg_branches.{i}.{k}"] = v
+        key = tuple((k, v.data_ptr(), v._version) for k, v in sd.items()) + (Q,)
+        if self._engine is None or key != self._engine_key:
+            l0 = self.layers[0]
+            self._engine = FusionDecoderEngine(sd, num_query=Q, embed_dims=self.embed_dims,
+                                               num_heads=l0.attentions[0].num_heads, num_layers=self.num_layers,
+                                               num_cams=l0.attentions[1].num_cams, pc_range=l0.attentions[1].pc_range,
+                                               precision=self.precision, device=query.device)
+            self._engine_key = key
+        eng = self._engine
+        feats, l2i, img_w, img_h, _, _ = eng.prepare_inputs(value, kwargs["img_metas"])
+
+        def rows(t, width):          # [Q,B,width] -> batch-major [B*Q,width]
+            return t.permute(1, 0, 2).reshape(B * Q, width).float().contiguous()
+
+        pos = rows(query_pos, C) if query_pos is not None else torch.zeros((B * Q, C), device=query.device)
+        ref = reference_points.reshape(B * Q, 3).float().contiguous()
+        eng._keep = []
+        hs, refs, *_ = eng.decoder(feats, l2i, img_w, img_h, B, keep_all=True, init=(rows(query, C), ref, pos),
+                                   refine=reg_branches is not None)
+        eng._keep = []
+        if self.return_intermediate:
+            return (torch.stack([h.view(B, Q, C).permute(1, 0, 2) for h in hs]),
+                    torch.stack([r.view(B, Q, 3) for r in refs]))
+        return hs[-1].view(B, Q, C).permute(1, 0, 2), refs[-1].view(B, Q, 3)
 
 
 @_register_everywhere(TRANSFORMER, "mmdet.models.utils.builder", "TRANSFORMER")
@@ -279,9 +321,10 @@ class Detr3DTransformer(nn.Module):
     reg_branches=None, **kwargs)`` -> ``(inter_states [L,Q,B,C], init_reference [B,Q,3], inter_references [L,B,Q,3])``."""
 
     def __init__(self, num_feature_levels=4, num_cams=6, two_stage_num_proposals=300, decoder=None, init_cfg=None,
-                 precision="bf16", **kwargs):
+                 precision="bf16x3", **kwargs):
         super().__init__()
         self.decoder = TRANSFORMER_LAYER_SEQUENCE.build(decoder)
+        self.decoder.precision = precision
         self.embed_dims = self.decoder.embed_dims
         self.num_feature_levels, self.num_cams = num_feature_levels, num_cams
         self.two_stage_num_proposals = two_stage_num_proposals
@@ -353,6 +396,17 @@ class NMSFreeCoder:
             keep = keep & (scores > self.score_threshold).to(torch.uint8)
         return boxes, scores, labels, keep
 
+    def decode_records(self, preds_dicts):
+        """One fixed-size record tensor ``[B, max_num, 12]`` (box, score, label, keep) written by the decode kernel:
+        what ``sharding.gather_results`` ships between ranks (no host sync, no pickling)."""
+        if self.post_center_range is None:
+            raise NotImplementedError("Need to reorganize output as a batch, only support post_center_range is not None for now!")
+        rec = ops.decode(preds_dicts["all_cls_scores"][-1], preds_dicts["all_bbox_preds"][-1], self.max_num,
+                         self.post_center_range, records=True)
+        if self.score_threshold:
+            rec[..., 11] *= (rec[..., 9] > self.score_threshold).to(rec.dtype)
+        return rec
+
     def decode(self, preds_dicts):
         boxes, scores, labels, keep = self.decode_padded(preds_dicts)
         out = []
@@ -392,15 +446,19 @@ class Detr3DHead(nn.Module):
 
     Differences by design: batch > 1 works; radar returns come in through ``img_metas[b]['radar_tokens']``
     (``[n,36]`` float32, see ``transcar_b200.radar_tokens``) instead of disk reads inside ``forward``;
-    extra ctor key ``precision`` ('bf16' tensor-core path, default, or 'fp32' parity mode)."""
+    extra ctor key ``precision``: 'bf16x3' (default: tensor cores on split-bf16 operands, within 1e-3 / 1e-2 of the
+    fp32 reference end to end), 'bf16' (one tensor-core pass, fastest) or 'fp32' (CUDA-core parity mode)."""
 
     def __init__(self, *args, with_box_refine=False, as_two_stage=False, transformer=None, bbox_coder=None,
                  num_cls_fcs=2, code_weights=None, num_classes=10, in_channels=256, num_query=900, num_reg_fcs=2,
                  sync_cls_avg_factor=False, positional_encoding=None, loss_cls=None, loss_bbox=None, loss_iou=None,
-                 train_cfg=None, test_cfg=None, init_cfg=None, code_size=10, precision="bf16", **kwargs):
+                 train_cfg=None, test_cfg=None, init_cfg=None, code_size=10, precision="bf16x3", **kwargs):
         super().__init__()
         if as_two_stage or not with_box_refine:
             raise NotImplementedError("transcar_b200.Detr3DHead: TransCAR configs use with_box_refine=True, as_two_stage=False")
+        if code_size != 10:
+            raise NotImplementedError("transcar_b200.Detr3DHead: code_size must be 10 (the radar mask reads box-code "
+                                      "columns 3, 6, 7 and the anchor update columns 0, 1, 4: detr3d_head.py:543-600)")
         self.with_box_refine, self.as_two_stage = with_box_refine, as_two_stage
         self.num_query, self.num_classes, self.in_channels = num_query, num_classes, in_channels
         self.num_reg_fcs, self.code_size = num_reg_fcs, code_size
@@ -468,6 +526,32 @@ class Detr3DHead(nn.Module):
             self._engine_key = key
         return self._engine
 
+    _FROZEN = ("transformer.", "cls_branches.", "reg_branches.", "query_embedding.")
+
+    def decoder_engine(self):
+        """Decoder-only engine for the training variant, keyed on the tensors it actually consumes (the frozen DETR3D
+        transformer, ``reg_branches`` and the query embedding): optimizer steps on the radar head do not rebuild it."""
+        named = {k: v for k, v in self.state_dict().items()
+                 if k.startswith(("transformer.", "reg_branches.", "query_embedding."))}
+        key = tuple((k, v.data_ptr(), v._version) for k, v in named.items())
+        if getattr(self, "_dec_engine", None) is None or key != self._dec_engine_key:
+            dev = self.query_embedding.weight.device
+            if dev.type != "cuda":
+                raise RuntimeError("transcar_b200.Detr3DHead: parameters must live on a CUDA device (no CPU fallback)")
+            layer0 = self.transformer.decoder.layers[0]
+            self._dec_engine = FusionDecoderEngine(
+                named, num_query=self.num_query, embed_dims=self.embed_dims, num_heads=layer0.attentions[0].num_heads,
+                num_layers=self.transformer.decoder.num_layers, num_cams=self.transformer.num_cams,
+                pc_range=self.pc_range, precision=self.precision, device=dev)
+            self._dec_engine_key = key
+        return self._dec_engine
+
+    def invalidate_engines(self):
+        """Drop the cached executors.  Needed only after weights were changed through ``p.data`` (which does not bump the
+        tensor version the caches are keyed on); ``load_state_dict`` / optimizer steps are detected automatically."""
+        self._engine = self._engine_key = None
+        self._dec_engine = self._dec_engine_key = None
+
     def forward(self, mlvl_feats, img_metas, return_aux=False):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self.forward_train(mlvl_feats, img_metas)
@@ -480,11 +564,16 @@ class Detr3DHead(nn.Module):
         ``loss.backward()`` fills ``.grad`` of the radar-head parameters.  Dropout (p = 0.1 in the reference configs) is
         not applied.  Parameters outside the radar head receive no gradient."""
         from .training import RadarHeadTrainer, radar_head_apply
-        eng = self.engine()
+        if any(p.requires_grad for n, p in self.named_parameters() if n.startswith(self._FROZEN)):
+            raise NotImplementedError(
+                "transcar_b200: only the radar head trains (reference recipe, tools/train.py:238-252); freeze "
+                "transformer.*, cls_branches.*, reg_branches.* and query_embedding.* (requires_grad_(False))")
+        eng = self.decoder_engine()
         with torch.no_grad():
-            feats, l2i, img_w, img_h, tokens, key_xy = eng.prepare_inputs(mlvl_feats, img_metas)
+            feats, l2i, img_w, img_h, tokens, key_xy = eng.prepare_inputs(mlvl_feats, img_metas, radar=True)
             B = feats[0].shape[0]
             eng._keep = []
+            # decoder() joins its side branch before returning: ref / code are safe to read on this stream
             _, _, x32, _, ref, code = eng.decoder(feats, l2i, img_w, img_h, B, keep_all=False)
             eng._keep = []
         named = dict(self.named_parameters())

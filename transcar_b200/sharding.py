@@ -108,17 +108,39 @@ class GradBucket:
         n = sum(p.numel() for p in self.params)
         self.n_scalars = n_scalars
         self.flat = torch.zeros(n + n_scalars, device=dev, dtype=torch.float32)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)      # gradients are written in place
+            self.views.append(self.flat[off: off + p.numel()].view_as(p))
             off += p.numel()
         self.scalars = self.flat[off:]
+        self._install()
+
+    def _install(self):
+        """Point every ``p.grad`` at its slice of the flat buffer (gradients are then written in place)."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def zero(self):
+        """Zero the bucket and re-install the aliases: ``optimizer.zero_grad(set_to_none=True)`` (torch's default) or any
+        ``p.grad = ...`` drops them, after which autograd would allocate fresh gradients outside the bucket."""
         self.flat.zero_()
+        self._install()
+
+    def _collect(self):
+        """Gradients that no longer alias the bucket (see ``zero``) are copied in, so ``all_reduce`` never reduces stale
+        zeros; the alias is restored."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+            p.grad = v
 
     def all_reduce(self, group=None, async_op=False):
         """Sum over ranks; gradients become the mean, the scalar slots stay sums divided by W (= reduce_mean)."""
+        self._collect()
         _, w = world()
         if w == 1:
             return None
