@@ -268,11 +268,14 @@ TC_API int tc_decode(const tc_decode_args* a, tc_stream_t stream);
  * Training variant: backward building blocks of the radar fusion head - the part of TransCAR that trains
  * (tools/train.py:238-252 freezes backbone, neck, DETR3D transformer, cls/reg branches and query embedding, so
  * gradients flow through H:531-536 and H:573-729 only).  The backward GEMMs are tc_linear calls on transposed
- * operands (dX = dY W: A = dY, W = W^T;  dW = dY^T X: A = dY^T, W = X^T); everything else is below.  Gradients that
+ * operands (dX = dY W: A = dY, W = W^T;  dW = dY^T X: A = dY^T, W = X^T) - on the tensor cores in bf16x3 mode, the
+ * transposes written directly as split-bf16 operands by tc_transpose; everything else is below.  Gradients that
  * are reductions (bias / LayerNorm parameters, dK / dV rows shared by many queries) are ACCUMULATED with fp32
  * atomics: the caller zeroes its gradient bucket once per step.
  */
-/* dst[c, r] = src[r, c]; dtypes fp32 or bf16 on either side (ld in elements). */
+/* dst[c, r] = src[r, c]; dtypes fp32 or bf16 on either side (ld in elements).  dst_dtype = TC_BF16X2 (fp32 source only)
+ * writes the split-bf16 transpose [cols, 2 * rows_pad] with rows_pad = ld_dst / 2 >= rows; columns rows..rows_pad-1 of both
+ * halves are zero-filled, so rows_pad can be the 64-aligned reduction length of a bf16x3 wgrad GEMM. */
 TC_API int tc_transpose(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst,
                  int32_t rows, int32_t cols, tc_stream_t stream);
 /* out[n] += sum_m x[m, n]   (bias gradient). */

@@ -463,3 +463,36 @@ def test_decode_vs_oracle(ops):
         torch.testing.assert_close(scores[b][k], want["scores"], rtol=0, atol=1e-6)
         assert torch.equal(labels[b][k].long(), want["labels"])
         torch.testing.assert_close(boxes[b][k], want["bboxes"], rtol=1e-6, atol=1e-5)
+
+
+def test_decode_ties_records_and_short_inputs(ops):
+    """Radix-select decode: exact ties at the selection threshold are broken by the lowest flat index (deterministic),
+    the single-tensor record output equals the four-tensor one, and fewer scores than max_num are zero-padded."""
+    rng = [-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]
+    B, Q = 2, 900
+    cls = torch.zeros((B, Q, 10), device=dev())                      # every score = 0.5: 9000-way tie
+    cls[0, 5, 3] = 2.0
+    cls[0, 700, 9] = 1.0
+    cls[1, :, 4] = -1.0                                               # sample 1: class 4 loses against the rest
+    code = rnd((B, Q, 10), 43)
+    boxes, scores, labels, keep = ops.decode(cls, code, 300, rng)
+    flat0 = torch.cat([torch.tensor([5 * 10 + 3, 700 * 10 + 9]), torch.tensor([i for i in range(400) if i not in (53,)][:298])])
+    assert torch.equal(labels[0].cpu().long(), flat0 % 10)
+    torch.testing.assert_close(scores[0, :3].cpu(), torch.tensor([2.0, 1.0, 0.0]).sigmoid(), rtol=0, atol=1e-7)
+    want1 = torch.tensor([i for i in range(400) if i % 10 != 4][:300])
+    assert torch.equal(labels[1].cpu().long(), want1 % 10)
+    torch.testing.assert_close(boxes[1, :, 0].cpu(), code[1, want1 // 10, 0].cpu(), rtol=0, atol=0)
+    rec = ops.decode(cls, code, 300, rng, records=True)
+    assert rec.shape == (B, 300, 12)
+    assert torch.equal(rec[..., :9], boxes) and torch.equal(rec[..., 9], scores)
+    assert torch.equal(rec[..., 10], labels.float()) and torch.equal(rec[..., 11], keep.float())
+    # fewer scores than max_num
+    b2, s2, l2, k2 = ops.decode(cls[:, :20].contiguous(), code[:, :20].contiguous(), 300, rng)
+    assert (k2[:, 200:] == 0).all() and (s2[:, 200:] == 0).all() and (b2[:, 200:] == 0).all()
+    assert (s2[:, :200] > 0).all()
+    # random scores once more against torch.topk (values; ties have measure zero)
+    cls3 = rnd((3, Q, 10), 44, 3.0)
+    _, s3, l3, _ = ops.decode(cls3, rnd((3, Q, 10), 45), 300, rng)
+    top, idx = cls3.sigmoid().view(3, -1).topk(300, dim=1)
+    torch.testing.assert_close(s3, top, rtol=0, atol=1e-7)
+    assert torch.equal(l3.long(), idx % 10)

@@ -34,6 +34,32 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ s
   }
 }
 
+// [R,C] fp32 -> split bf16 [C, 2*Rp] (TC_BF16X2: hi | lo halves of Rp columns each); rows R..Rp-1 are written as zeros so
+// that Rp can be the 64-aligned reduction length of a bf16x3 wgrad GEMM (dW = dY^T X reduces over the M rows).
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ src, long long ld_src,
+                                                              __nv_bfloat16* __restrict__ dst, long long ld_dst, int rows,
+                                                              int rows_pad, int cols) {
+  __shared__ float tile[32][33];
+  pdl_trigger();
+  pdl_wait();
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[(long long)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows_pad) {
+      const float v = tile[tx][i];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      dst[(long long)c * ld_dst + r] = hi;
+      dst[(long long)c * ld_dst + rows_pad + r] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+}
+
 // ---- column sum --------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx, int M, int N, float* __restrict__ out) {
@@ -307,11 +333,21 @@ extern "C" int tc_transpose(const void* src, int32_t src_dtype, int64_t ld_src, 
   using namespace tc;
   TC_REQUIRE(src && dst, TC_ERR_NULL, "tc_transpose: NULL pointer");
   TC_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= rows, TC_ERR_SHAPE, "tc_transpose: bad shape");
+  cudaStream_t s = as_stream(stream);
+  if (dst_dtype == TC_BF16X2) {            // split output [cols, 2 * rows_pad], rows_pad = ld_dst / 2 (zero padded)
+    TC_REQUIRE(src_dtype == TC_F32, TC_ERR_DTYPE, "tc_transpose: a split (TC_BF16X2) destination needs an fp32 source");
+    TC_REQUIRE(ld_dst % 2 == 0 && ld_dst / 2 >= rows, TC_ERR_SHAPE, "tc_transpose: split destination needs ld_dst = 2 * rows_pad >= 2 * rows");
+    if (cols == 0 || ld_dst == 0) return TC_OK;
+    const int rows_pad = (int)(ld_dst / 2);
+    launch(transpose_split_kernel, dim3((cols + 31) / 32, (rows_pad + 31) / 32), dim3(256), 0, s, 1u, (const float*)src,
+           (long long)ld_src, (__nv_bfloat16*)dst, (long long)ld_dst, rows, rows_pad, cols);
+    count_launch();
+    return check_launch("tc_transpose(split)");
+  }
   TC_REQUIRE((src_dtype == TC_F32 || src_dtype == TC_BF16) && (dst_dtype == TC_F32 || dst_dtype == TC_BF16), TC_ERR_DTYPE,
              "tc_transpose: bad dtype");
   if (rows == 0 || cols == 0) return TC_OK;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-  cudaStream_t s = as_stream(stream);
   const bool si = src_dtype == TC_BF16, di = dst_dtype == TC_BF16;
   if (!si && !di) launch(transpose_kernel<float, float>, grid, dim3(256), 0, s, 1u, (const float*)src, (long long)ld_src, (float*)dst, (long long)ld_dst, rows, cols);
   else if (!si && di) launch(transpose_kernel<float, __nv_bfloat16>, grid, dim3(256), 0, s, 1u, (const float*)src, (long long)ld_src, (__nv_bfloat16*)dst, (long long)ld_dst, rows, cols);

@@ -69,7 +69,7 @@ struct EpiParams {
   __nv_bfloat16* out_bf16; long long ld_out_bf16;
   int out16;      // TC_BF16, TC_BF16X2 (hi at column n, lo at column N + n) or TC_F16
   int vec;        // 1: every row-wise operand is 32-byte aligned with a 32-byte multiple pitch -> 256-bit accesses
-  int has_init;   // bias / row_bias / residual(s) are folded into the accumulator before the first MMA
+  int has_init;   // row_bias / residual(s) present
 };
 
 // ---- row-per-thread global access: 32 consecutive floats of one row ---------------------------------
@@ -88,18 +88,20 @@ __device__ __forceinline__ void st256u(void* p, const uint32_t* v) {
                ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-// v[j] += row[j], j < 32 (ncols valid columns)
+// v[j] += row[j], j < 32 (ncols valid columns); 256-bit loads for every complete group of 8 columns
 __device__ __forceinline__ void add_row32(const float* row, int ncols, bool vec, float (&v)[32]) {
-  if (vec && ncols >= 32) {
-    float t[32];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ld256(row + 8 * i, t + 8 * i);
+  for (int i = 0; i < 4; ++i) {
+    if (vec && 8 * i + 8 <= ncols) {
+      float t[8];
+      ld256(row + 8 * i, t);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += t[j];
-  } else {
+      for (int j = 0; j < 8; ++j) v[8 * i + j] += t[j];
+    } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) v[j] += row[j];
+      for (int j = 8 * i; j < 8 * i + 8; ++j)
+        if (j < ncols) v[j] += row[j];
+    }
   }
 }
 
@@ -156,8 +158,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   float* s_beta = s_gamma + BN;
   float2* s_part = reinterpret_cast<float2*>(smem + kOffPart);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), accbar = smem_u32(bars + 2 * kStages),
-                 initbar = smem_u32(bars + 2 * kStages + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), accbar = smem_u32(bars + 2 * kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
@@ -167,7 +168,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(accbar, 1);
-    mbar_init(initbar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -207,12 +207,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // kind::f16 instruction descriptor: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), K-major A and B,
       // N>>3 at bit 17, M>>4 at bit 24
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // slow path only (unaligned rows / partial N tile): accumulator pre-loaded with bias + residuals by the epilogue warps
-      const bool init_in_tmem = p.has_init && !(p.vec && min(BN, p.N - n0) == BN);
-      if (init_in_tmem) {
-        mbar_wait(initbar, 0);
-        tc_fence_after();
-      }
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -224,7 +218,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint64_t dwh = make_desc_sw128(a_addr + 2 * kABytes), dwl = make_desc_sw128(a_addr + 2 * kABytes + kBBytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_base, dah + 2 * k, dwh + 2 * k, idesc, ((int)init_in_tmem | kb | k) ? 1u : 0u);
+            umma_bf16(tmem_base, dah + 2 * k, dwh + 2 * k, idesc, (kb | k) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, dal + 2 * k, dwh + 2 * k, idesc, 1u);
 #pragma unroll
@@ -233,7 +227,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + kABytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)          // +32 bytes (2 x 16 B) per UMMA_K step inside the 128 B row
-            umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, ((int)init_in_tmem | kb | k) ? 1u : 0u);
+            umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);               // frees the smem slot once these MMAs retire
       }
@@ -265,68 +259,38 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
     }
 
-    // input-side terms of columns [c*32, c*32+32): (gate ? bias + row_bias : 0) + residual + residual2
-    auto side_terms = [&](int c, bool with_gated, float (&v)[32]) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      if (!row_ok) return;
-      const int nc = ncols - c * 32;
-      if (with_gated) {
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = s_bias[c * 32 + j];
-        }
-        if (p.row_bias) add_row32(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n0 + c * 32, nc, vec, v);
-      }
-      if (p.residual) add_row32(p.residual + (long long)m * p.ld_residual + n0 + c * 32, nc, vec, v);
-      if (p.residual2) add_row32(p.residual2 + (long long)m * p.ld_residual2 + n0 + c * 32, nc, vec, v);
-    };
-
-    // Input-side terms (bias, per-query row bias, residuals) do not depend on the product.  Fast path: they are requested
-    // right here, while the operands are in flight and the MMAs run, stay in registers (64 per thread) and are added to the
-    // accumulator afterwards.  (Folding them into the accumulator BEFORE the MMAs - the first version - made the MMAs wait
-    // for these loads: measured 4400 cycles for one fp32 residual tile vs 2100 for operands + MMAs, clock64.)
+    // Input-side terms (bias, per-query row bias, residuals) do not depend on the product.  Fast path (full tile, 32-byte
+    // aligned rows): they are requested right here, while the operands are in flight and the MMAs run, stay in registers
+    // (64 per thread) and are added to the accumulator afterwards.  (Folding them into the accumulator BEFORE the MMAs -
+    // the first version - made the MMAs wait for these loads: measured 4400 cycles for one fp32 residual tile vs 2100 for
+    // operands + MMAs, clock64.)  Partial tiles / unaligned rows fetch them after the accumulator is complete.
     const bool side_regs = p.has_init && vec && ncols == BN;
     float side[BN];
 #pragma unroll
     for (int j = 0; j < BN; ++j) side[j] = 0.f;
-    if (side_regs) {
-      if (row_ok) {
-        auto add64 = [&](const float* src) {
-          float t[BN];
+    if (side_regs && row_ok) {
+      auto add64 = [&](const float* src) {
+        float t[BN];
 #pragma unroll
-          for (int i = 0; i < BN / 8; ++i) ld256(src + 8 * i, t + 8 * i);
+        for (int i = 0; i < BN / 8; ++i) ld256(src + 8 * i, t + 8 * i);
 #pragma unroll
-          for (int j = 0; j < BN; ++j) side[j] += t[j];
-        };
-        if (gate) {
-          if (p.bias) {
+        for (int j = 0; j < BN; ++j) side[j] += t[j];
+      };
+      if (gate) {
+        if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < BN; ++j) side[j] = s_bias[j];
-          }
-          if (p.row_bias) add64(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n0);
+          for (int j = 0; j < BN; ++j) side[j] = s_bias[j];
         }
-        if (p.residual) add64(p.residual + (long long)m * p.ld_residual + n0);
-        if (p.residual2) add64(p.residual2 + (long long)m * p.ld_residual2 + n0);
+        if (p.row_bias) add64(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n0);
       }
-    } else if (p.has_init) {
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        uint32_t r[32];
-        side_terms(c, gate, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-        tmem_st32(trow + c * 32, r);
-      }
-      tc_fence_before();
-      mbar_arrive(initbar);
+      if (p.residual) add64(p.residual + (long long)m * p.ld_residual + n0);
+      if (p.residual2) add64(p.residual2 + (long long)m * p.ld_residual2 + n0);
     }
 
     mbar_wait(accbar, 0);
     tc_fence_after();
 
-    // pre-activation row chunk: accumulator (+ bias when it was not folded in); gated-off rows keep only the residuals
+    // pre-activation row chunk:  (gate ? acc + bias + row_bias : 0) + residual + residual2
     auto load_chunk = [&](int c, float (&v)[32]) {       // c must be a compile-time constant (side[] lives in registers)
       uint32_t r[32];
       tmem_ld32(trow + c * 32, r);
@@ -336,12 +300,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         return;
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (!p.has_init && p.bias) {
+      for (int j = 0; j < 32; ++j) v[j] = gate ? __uint_as_float(r[j]) : 0.f;
+      if (gate && p.bias) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += s_bias[c * 32 + j];
       }
-      if (!gate) side_terms(c, false, v);
+      if (!p.has_init || !row_ok) return;
+      const int nc = ncols - c * 32;
+      if (gate && p.row_bias) add_row32(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n0 + c * 32, nc, vec, v);
+      if (p.residual) add_row32(p.residual + (long long)m * p.ld_residual + n0 + c * 32, nc, vec, v);
+      if (p.residual2) add_row32(p.residual2 + (long long)m * p.ld_residual2 + n0 + c * 32, nc, vec, v);
     };
     auto store_chunk = [&](int c, float (&v)[32]) {
       const int nc = ncols - c * 32;
@@ -374,11 +342,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       } else {
+        if (p.out_f32) {
+          float* dst = p.out_f32 + (long long)m * p.ld_out_f32 + n;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nc) {
-            if (p.out_f32) p.out_f32[(long long)m * p.ld_out_f32 + n + j] = v[j];
-            if (p.out_bf16) {
+          for (int i = 0; i < 4; ++i) {
+            if (vec && 8 * i + 8 <= nc) {
+              st256(dst + 8 * i, v + 8 * i);
+            } else {
+#pragma unroll
+              for (int j = 8 * i; j < 8 * i + 8; ++j)
+                if (j < nc) dst[j] = v[j];
+            }
+          }
+        }
+        if (p.out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nc) {
               __nv_bfloat16* d16 = p.out_bf16 + (long long)m * p.ld_out_bf16 + n + j;
               if (p.out16 == TC_F16) {
                 *reinterpret_cast<__half*>(d16) = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));

@@ -190,6 +190,18 @@ class FusionDecoderEngine:
             raise RuntimeError("transcar_b200: feature levels disagree in dtype")
         return out
 
+    def _upload_feats(self, host_feats):
+        """Host feature maps -> STATIC device buffers (allocated once per shape / layout / dtype, so the CUDA graph keyed
+        on their addresses is reused every frame); asynchronous when the host tensors are pinned."""
+        key = tuple((tuple(f.shape), tuple(f.stride()), f.dtype) for f in host_feats)
+        bufs = self._pinned.get(("feats", key))
+        if bufs is None:
+            bufs = self._pinned[("feats", key)] = [
+                torch.empty_strided(f.shape, f.stride(), dtype=f.dtype, device=self.device) for f in host_feats]
+        for b, f in zip(bufs, host_feats):
+            b.copy_(f, non_blocking=True)
+        return bufs
+
     def _staging(self, name, shape):
         """Pinned host buffer for one small per-frame input, allocated once per (name, shape).  The previous upload from it
         is awaited before the host overwrites it."""
@@ -442,7 +454,7 @@ class FusionDecoderEngine:
         if len(img_metas) != B:
             raise ValueError(f"img_metas has {len(img_metas)} entries for a batch of {B}")
         if not mlvl_feats[0].is_cuda:
-            mlvl_feats = [f.to(self.device, non_blocking=True) for f in mlvl_feats]
+            mlvl_feats = self._upload_feats(mlvl_feats)
         feats = self._prep_feats(mlvl_feats)
         l2i, img_w, img_h = self._prep_metas(img_metas, B)
         radar = self.has_radar if radar is None else radar

@@ -436,6 +436,19 @@ def transpose(src, out_dtype=None, out=None):
     return out
 
 
+def transpose_split(src, pad_to=64):
+    """fp32 [R,C] -> :class:`SplitBf16` of the transpose, logical [C, Rp] with Rp = R rounded up to ``pad_to`` (zero padded):
+    an operand of a bf16x3 GEMM that reduces over R."""
+    lib = _lib.load()
+    s2, lds = _rows(_need(src, "src", torch.float32), "src")
+    R, Cc = s2.shape
+    Rp = (R + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((Cc, 2 * Rp), device=s2.device, dtype=torch.bfloat16)
+    _lib.check(_call("transpose_split", lib.tc_transpose, _ptr(s2), TC_F32, lds, _ptr(out), TC_BF16X2, 2 * Rp, R, Cc, _stream()),
+               "transpose_split")
+    return SplitBf16(out)
+
+
 def colsum_(x, out):
     """out[n] += sum_m x[m,n]  (out: fp32 [N], accumulated in place)."""
     lib = _lib.load()

@@ -580,7 +580,8 @@ class Detr3DHead(nn.Module):
         key = tuple(p.data_ptr() for p in named.values())
         if getattr(self, "_trainer", None) is None or self._trainer_key != key:
             live = {k: v.data for k, v in named.items() if v.dtype == torch.float32}
-            self._trainer = RadarHeadTrainer(live, num_heads=8, pc_range=self.pc_range)
+            self._trainer = RadarHeadTrainer(live, num_heads=8, pc_range=self.pc_range,
+                                             tensor_cores=self.precision != "fp32")
             self._trainer_key = key
         cls_all, reg_all = radar_head_apply(self._trainer, named, x32.float(), ref, code, tokens, key_xy, B)
         return dict(all_cls_scores=cls_all, all_bbox_preds=reg_all, enc_cls_scores=None, enc_bbox_preds=None)

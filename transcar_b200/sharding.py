@@ -32,6 +32,32 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def bind_to_gpu_numa(local_rank: int, only_multi_process: bool = True):
+    """Pin this process (and the pinned host buffers it allocates afterwards: first touch) to the CPUs of the NUMA node
+    its GPU hangs off, so that N ranks staging feature maps at once do not all pull from one socket's memory.  Returns
+    the node, or None when the topology is not exposed (containers without /sys PCI entries) or the job is single-process
+    (``only_multi_process``: the host-side baselines of a 1-GPU bench keep every core)."""
+    import os
+    if only_multi_process and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return None
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_bounds(n_samples: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous, balanced slice of ``n_samples`` owned by ``rank``: the first ``n % W`` ranks take one
     extra sample.  Contiguous (not strided) so that the gathered result is already in dataset order."""

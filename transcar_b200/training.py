@@ -13,7 +13,13 @@ masked attention ``tc_attention_fwd`` (sparse); backward GEMMs are ``tc_linear``
 (``dX = dY W`` with the running gradient fused in as the residual, ``dW = dY^T X``), plus ``tc_colsum``,
 ``tc_layernorm_bwd``, ``tc_mask_grad`` and ``tc_attention_sparse_bwd``.  Masks are not differentiable; the only cross-layer
 gradient paths are the residual stream and ``reg_l[:, (0,1,4)] += reg_{l-1}[:, (0,1,4)]`` (H:664-665, H:722-723), whose
-backward is one ``tc_box_anchor_add`` on the gradients.  Arithmetic is fp32 (the reference trains this head in fp32).
+backward is one ``tc_box_anchor_add`` on the gradients.
+
+GEMM arithmetic: ``tensor_cores=True`` (default whenever the head runs a tensor-core precision mode) evaluates every
+forward, dgrad and wgrad GEMM whose reduction length allows it on tcgen05 in bf16x3 (split-bf16 operands, fp32
+accumulation: ~1e-5 of fp32, the reference trains this head in fp32); the operands of the backward GEMMs - dY^T, X^T, W^T -
+are written directly as split-bf16 matrices by ``tc_transpose`` (the wgrad reduction over the B*Q rows is zero-padded to a
+multiple of 64).  ``tensor_cores=False`` keeps everything on the exact fp32 CUDA-core path (parity mode).
 
 Data parallel: every rank runs its own samples; ``sharding.GradBucket`` all-reduces the flat gradient buffer once per step.
 """
@@ -40,9 +46,11 @@ def trainable_names(state_dict_keys):
 class RadarHeadTrainer:
     """fp32 forward/backward of the radar fusion head over batch-major ``[B*Q, C]`` activations."""
 
-    def __init__(self, params, num_heads=8, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)):
+    def __init__(self, params, num_heads=8, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), tensor_cores=True):
         """``params``: dict name -> fp32 CUDA tensor (the live parameters, reference key names)."""
         self.p = params
+        self.tc = tensor_cores
+        self._wcache = {}                   # split-bf16 copies of the weights, valid for one forward / backward
         self.heads = num_heads
         self.pc_range = [float(v) for v in pc_range]
         self.names = trainable_names(params.keys())
@@ -57,13 +65,26 @@ class RadarHeadTrainer:
             off += t.numel()
         self.ctx = None
 
+    # ------------------------------------------------------------------ GEMM plumbing
+    def _wsplit(self, wkey, w_rows, W, transposed):
+        """Split-bf16 copy of a weight (or of its transpose) for this step; the parameters change between steps."""
+        key = (wkey, w_rows, transposed)
+        t = self._wcache.get(key)
+        if t is None:
+            t = self._wcache[key] = ops.transpose_split(W) if transposed else ops.cast_split(W)
+        return t
+
     # ------------------------------------------------------------------ differentiable pieces (forward records a tape)
     def _linear(self, tape, x, wkey, bkey, relu=False, residual=None, gate=None, w_rows=None):
         """y = [relu]( gate * (x W^T + b) + residual ).  ``w_rows`` selects a row range of a packed weight/bias."""
         W, b = self.p[wkey], self.p[bkey]
         if w_rows is not None:
             W, b = W[w_rows[0]:w_rows[1]], b[w_rows[0]:w_rows[1]]
-        y, _ = ops.linear(x, W, b, relu=relu, residual=residual, row_gate=gate)
+        if self.tc and x.shape[1] % 64 == 0:
+            y, _ = ops.linear(ops.cast_split(x), self._wsplit(wkey, w_rows, W, False), b, relu=relu, residual=residual,
+                              row_gate=gate)
+        else:               # K = 3 / 36 (raw radar fields): exact fp32 CUDA-core path
+            y, _ = ops.linear(x, W, b, relu=relu, residual=residual, row_gate=gate)
         tape.append(("linear", x, wkey, bkey, w_rows, y if relu else None, gate))
         return y
 
@@ -75,12 +96,18 @@ class RadarHeadTrainer:
         if w_rows is not None:
             W, gW, gb = W[w_rows[0]:w_rows[1]], gW[w_rows[0]:w_rows[1]], gb[w_rows[0]:w_rows[1]]
         ops.colsum_(dy, gb)
-        dyT, xT = ops.transpose(dy), ops.transpose(x)                      # [N,M], [K,M]
-        ops.linear(dyT, xT, None, out_f32=gW)                              # dW = dY^T X
+        if self.tc:         # dW = dY^T X on tcgen05: both operands transposed straight into split-bf16, M padded to 64
+            ops.linear(ops.transpose_split(dy), ops.transpose_split(x), None, out_f32=gW)
+        else:
+            dyT, xT = ops.transpose(dy), ops.transpose(x)                  # [N,M], [K,M]
+            ops.linear(dyT, xT, None, out_f32=gW)                          # dW = dY^T X
         if not need_dx:
             return None
-        WT = ops.transpose(W)                                              # [K,N]
-        dx, _ = ops.linear(dy, WT, None, residual=dx_accum)                # dX = dY W (+ running gradient)
+        if self.tc and dy.shape[1] % 64 == 0:
+            dx, _ = ops.linear(ops.cast_split(dy), self._wsplit(wkey, w_rows, W, True), None, residual=dx_accum)
+        else:               # N = 10 (box / class logits): exact fp32 CUDA-core path
+            WT = ops.transpose(W)                                          # [K,N]
+            dx, _ = ops.linear(dy, WT, None, residual=dx_accum)            # dX = dY W (+ running gradient)
         return dx
 
     def _ln(self, tape, x, key, relu=False):
@@ -103,6 +130,7 @@ class RadarHeadTrainer:
         Q = M // B
         R = tokens.shape[1]
         dev = x0.device
+        self._wcache = {}
         ctx = dict(B=B, Q=Q, R=R, C=C, enc=[], layers=[])
         # ---- radar encoders (H:531-536)
         t2 = tokens.reshape(B * R, NUM_RADAR_FEATS)
@@ -117,8 +145,13 @@ class RadarHeadTrainer:
         f = self._linear(enc, f, "radar_feat_encoder.2.weight", "radar_feat_encoder.2.bias", relu=True)
         self._linear(enc, f, "radar_feat_encoder.4.weight", "radar_feat_encoder.4.bias", relu=True)   # taped: ReLU mask
         # kvfeat = pos + relu(feat) (H:536): the same small GEMM once more with the sum fused as its post-add epilogue
-        kvfeat_sum, _ = ops.linear(f, self.p["radar_feat_encoder.4.weight"], self.p["radar_feat_encoder.4.bias"], relu=True,
-                                   post_add=pos)
+        if self.tc:
+            kvfeat_sum, _ = ops.linear(ops.cast_split(f), self._wsplit("radar_feat_encoder.4.weight", None,
+                                                                       self.p["radar_feat_encoder.4.weight"], False),
+                                       self.p["radar_feat_encoder.4.bias"], relu=True, post_add=pos)
+        else:
+            kvfeat_sum, _ = ops.linear(f, self.p["radar_feat_encoder.4.weight"], self.p["radar_feat_encoder.4.bias"], relu=True,
+                                       post_add=pos)
         ctx["n_pos"] = n_pos
         ctx["kvfeat"] = kvfeat_sum
         cls_all = torch.empty((3, B, Q, 10), device=dev, dtype=torch.float32)
@@ -209,6 +242,7 @@ class RadarHeadTrainer:
         dp = self._ln_bwd(enc[1], dp)
         self._linear_bwd(enc[0], dp, need_dx=False)
         self.ctx = None
+        self._wcache = {}
         return self.g
 
 
