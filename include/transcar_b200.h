@@ -324,6 +324,68 @@ typedef struct {
 } tc_attention_bwd_args;
 TC_API int tc_attention_sparse_bwd(const tc_attention_bwd_args* a, tc_stream_t stream);
 
+/* Backward of K1 (the "grid_sample scatter" of the training variant).  Replaces autograd through T:367-373 + T:381-422:
+ * F.grid_sample backward (bilinear, zeros padding, align_corners=False) for the four levels, the sigmoid-weighted masked
+ * sum and the projection chain, in one kernel over the same (query, valid camera, level, corner) set as the forward.
+ *   feat / ref / lidar2img / attn_logits / pc_range / img_w / img_h: exactly the forward's inputs (tc_sample_args)
+ *   dout      [B, Q, C] fp32         upstream gradient of the forward's `out`
+ *   d_feat[l] [B, N, H_l, W_l, C] fp32 channels-last, optional (all four or none): ACCUMULATED with fp32 atomics
+ *   d_logits  [B, Q, N*L] fp32, optional: written (0 for cameras that fail the validity test)
+ *   d_ref     [B, Q, 3] fp32, optional: written; gradient w.r.t. the normalised reference points (layer 0 of the decoder is
+ *             the only layer whose reference points are not detached, T:203)
+ */
+typedef struct {
+  const void* feat[TC_MAX_LEVELS];
+  int32_t H[TC_MAX_LEVELS];
+  int32_t W[TC_MAX_LEVELS];
+  int32_t num_levels;
+  int32_t B, N, Q, C;
+  int32_t feat_dtype;
+  const float* ref;
+  const float* lidar2img;
+  const float* attn_logits;
+  float pc_range[6];
+  float img_w, img_h;
+  const float* dout;
+  float* d_feat[TC_MAX_LEVELS];
+  float* d_logits;
+  float* d_ref;
+} tc_sample_bwd_args;
+TC_API int tc_sample_bwd(const tc_sample_bwd_args* a, tc_stream_t stream);
+
+/* Backward of the dense (mask-free) attention core of the decoder self-attention, fp32 operands: softmax statistics are
+ * recomputed from q, k (nothing but q, k, v, o is kept from the forward).  Replaces autograd through the baddbmm ->
+ * softmax -> bmm core of nn.MultiheadAttention (mmcv wrapper of cfg detr3d_res101_gridmask.py:68-72).
+ *   q, o, dout [B, Lq, heads*D]; k, v [B, Lk, heads*D] (row strides ld*, batch strides *_batch_stride, elements)
+ *   dq [B, Lq, heads*D], dk / dv [B, Lk, heads*D]: written (contiguous, row stride heads*D)
+ *   workspace: 2 * B * heads * Lq floats (log-sum-exp and <dout, o> per query row and head)
+ */
+typedef struct {
+  const float* q; const float* k; const float* v; const float* o; const float* dout;
+  int64_t ldq, ldk, ldv, ldo, ld_dout;
+  int64_t q_batch_stride, k_batch_stride, v_batch_stride, o_batch_stride, dout_batch_stride;
+  int32_t B, Lq, Lk, heads, D;
+  float scale;
+  float* dq; float* dk; float* dv;
+  float* workspace;
+} tc_attention_dense_bwd_args;
+TC_API int tc_attention_dense_bwd(const tc_attention_dense_bwd_args* a, tc_stream_t stream);
+
+/* Pointwise pieces of the decoder's training variant (T:17-32 inverse_sigmoid, T:122-123 / T:195-203 sigmoid), n elements:
+ *   TC_PW_LOGIT_BWD    out = grad * d inverse_sigmoid(x) / dx   (torch.clamp gradients: zero outside [0,1] / below eps)
+ *   TC_PW_SIGMOID_BWD  out = grad * y (1 - y)                   (x = the sigmoid OUTPUT y)
+ *   TC_PW_LOGIT        out = inverse_sigmoid(x)                 (grad ignored, may be NULL)
+ *   TC_PW_SIGMOID      out = sigmoid(x)                         (grad ignored, may be NULL) */
+enum { TC_PW_LOGIT_BWD = 0, TC_PW_SIGMOID_BWD = 1, TC_PW_LOGIT = 2, TC_PW_SIGMOID = 3 };
+TC_API int tc_pointwise(const float* grad, const float* x, float* out, int32_t n, int32_t mode, tc_stream_t stream);
+
+/* out[m, :] = a[m, :] + b[m % period, :]   ([M, N] fp32, contiguous; out may alias a).  The query_pos broadcast of the
+ * decoder's training forward (q = k = x + query_pos) and gradient sums. */
+TC_API int tc_add_rows(const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t period, tc_stream_t stream);
+/* out[r, :] += sum_b x[b * period + r, :]   (x [B*period, N] -> out [period, N]): gradients of batch-broadcast parameters
+ * (query embedding, T:119-121). */
+TC_API int tc_period_sum(const float* x, float* out, int32_t batches, int32_t period, int32_t N, tc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

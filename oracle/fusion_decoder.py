@@ -186,7 +186,7 @@ def transformer(sd, mlvl_feats, img_metas, num_layers=6, capture=None):
         new = torch.zeros_like(ref)
         new[..., :2] = tmp[..., :2] + logit(ref[..., :2])
         new[..., 2:3] = tmp[..., 4:5] + logit(ref[..., 2:3])
-        ref = new.sigmoid()
+        ref = new.sigmoid().detach()                               # T:203: the refined points carry no gradient onwards
         hs.append(x)
         refs.append(ref)
         if capture is not None:

@@ -108,6 +108,26 @@ class AttentionBwdArgs(C.Structure):
                 ("dk", _vp), ("dv", _vp), ("ld_dk", _i64), ("ld_dv", _i64), ("dk_batch_stride", _i64), ("dv_batch_stride", _i64)]
 
 
+class SampleBwdArgs(C.Structure):
+    _fields_ = [("feat", _vp * TC_MAX_LEVELS), ("H", _i32 * TC_MAX_LEVELS), ("W", _i32 * TC_MAX_LEVELS),
+                ("num_levels", _i32), ("B", _i32), ("N", _i32), ("Q", _i32), ("C", _i32),
+                ("feat_dtype", _i32),
+                ("ref", _vp), ("lidar2img", _vp), ("attn_logits", _vp),
+                ("pc_range", _f32 * 6), ("img_w", _f32), ("img_h", _f32),
+                ("dout", _vp), ("d_feat", _vp * TC_MAX_LEVELS), ("d_logits", _vp), ("d_ref", _vp)]
+
+
+class AttentionDenseBwdArgs(C.Structure):
+    _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("o", _vp), ("dout", _vp),
+                ("ldq", _i64), ("ldk", _i64), ("ldv", _i64), ("ldo", _i64), ("ld_dout", _i64),
+                ("q_batch_stride", _i64), ("k_batch_stride", _i64), ("v_batch_stride", _i64), ("o_batch_stride", _i64),
+                ("dout_batch_stride", _i64),
+                ("B", _i32), ("Lq", _i32), ("Lk", _i32), ("heads", _i32), ("D", _i32),
+                ("scale", _f32),
+                ("dq", _vp), ("dk", _vp), ("dv", _vp),
+                ("workspace", _vp)]
+
+
 # every symbol include/transcar_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "tc_abi_version": (C.c_int, []),
@@ -133,6 +153,11 @@ SYMBOLS = {
     "tc_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdArgs), _vp]),
     "tc_mask_grad": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),
     "tc_attention_sparse_bwd": (C.c_int, [C.POINTER(AttentionBwdArgs), _vp]),
+    "tc_sample_bwd": (C.c_int, [C.POINTER(SampleBwdArgs), _vp]),
+    "tc_attention_dense_bwd": (C.c_int, [C.POINTER(AttentionDenseBwdArgs), _vp]),
+    "tc_pointwise": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "tc_add_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "tc_period_sum": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

@@ -328,6 +328,221 @@ __global__ void __launch_bounds__(kWarps * 32) attention_sparse_bwd_kernel(const
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------ C ABI
+namespace tc {
+namespace {
+
+// ---- dense attention backward (decoder self-attention, fp32, head dim 32) ------------------------------------------------
+// Two kernels, both tile the "other" side through shared memory (32 rows of 32 floats per operand):
+//   stats + dq : one thread per query row of a (sample, head): pass 1 recomputes the softmax statistics (row maximum and
+//                sum -> log-sum-exp), pass 2 accumulates dq = scale * sum_j ds_ij k_j with ds = p (dp - delta),
+//                dp = <dout_i, v_j>, delta = <dout_i, o_i>; lse and delta are written to the workspace for
+//   dk / dv    : one thread per key row: dv_j = sum_i p_ij dout_i, dk_j = scale * sum_i ds_ij q_i.
+// nn.MultiheadAttention scales q before QK^T: s_ij = <scale * q_i, k_j>.
+struct DenseBwdParams {
+  const float* q; const float* k; const float* v; const float* o; const float* dout;
+  long long ldq, ldk, ldv, ldo, ldd, qbs, kbs, vbs, obs, dbs;
+  int B, Lq, Lk, heads;
+  float scale;
+  float* dq; float* dk; float* dv; float* lse; float* delta;
+};
+constexpr int kBwdRows = 128, kBwdTile = 32, kHD = 32;
+
+__global__ void __launch_bounds__(kBwdRows) attn_dense_bwd_dq_kernel(const DenseBwdParams p) {
+  __shared__ float sk[kBwdTile][kHD + 1];
+  __shared__ float sv[kBwdTile][kHD + 1];
+  const int i = blockIdx.x * kBwdRows + threadIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const bool ok = i < p.Lq;
+  float q[kHD], go[kHD], acc[kHD];
+  float delta = 0.f;
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) {
+    q[d] = ok ? p.q[(long long)b * p.qbs + (long long)i * p.ldq + h * kHD + d] * p.scale : 0.f;
+    go[d] = ok ? p.dout[(long long)b * p.dbs + (long long)i * p.ldd + h * kHD + d] : 0.f;
+    const float ov = ok ? p.o[(long long)b * p.obs + (long long)i * p.ldo + h * kHD + d] : 0.f;
+    delta = fmaf(go[d], ov, delta);
+    acc[d] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    const float lse = m + logf(l);                       // valid in pass 1
+    for (int j0 = 0; j0 < p.Lk; j0 += kBwdTile) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < kBwdTile * kHD; e += kBwdRows) {
+        const int r = e / kHD, d = e % kHD, j = j0 + r;
+        sk[r][d] = j < p.Lk ? p.k[(long long)b * p.kbs + (long long)j * p.ldk + h * kHD + d] : 0.f;
+        sv[r][d] = j < p.Lk ? p.v[(long long)b * p.vbs + (long long)j * p.ldv + h * kHD + d] : 0.f;
+      }
+      __syncthreads();
+      const int nj = min(kBwdTile, p.Lk - j0);
+      for (int r = 0; r < nj; ++r) {
+        float sc = 0.f;
+#pragma unroll
+        for (int d = 0; d < kHD; ++d) sc = fmaf(q[d], sk[r][d], sc);
+        if (pass == 0) {
+          const float mn = fmaxf(m, sc);
+          l = l * expf(m - mn) + expf(sc - mn);
+          m = mn;
+        } else {
+          const float pij = expf(sc - lse);
+          float dp = 0.f;
+#pragma unroll
+          for (int d = 0; d < kHD; ++d) dp = fmaf(go[d], sv[r][d], dp);
+          const float ds = pij * (dp - delta);
+#pragma unroll
+          for (int d = 0; d < kHD; ++d) acc[d] = fmaf(ds, sk[r][d], acc[d]);
+        }
+      }
+    }
+  }
+  if (!ok) return;
+  const long long row = ((long long)b * p.heads + h) * p.Lq + i;
+  p.lse[row] = m + logf(l);
+  p.delta[row] = delta;
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) p.dq[((long long)b * p.Lq + i) * (p.heads * kHD) + h * kHD + d] = acc[d] * p.scale;
+}
+
+__global__ void __launch_bounds__(kBwdRows) attn_dense_bwd_dkv_kernel(const DenseBwdParams p) {
+  __shared__ float sq[kBwdTile][kHD + 1];
+  __shared__ float sg[kBwdTile][kHD + 1];
+  __shared__ float s_lse[kBwdTile], s_delta[kBwdTile];
+  const int j = blockIdx.x * kBwdRows + threadIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const bool ok = j < p.Lk;
+  float k[kHD], v[kHD], dk[kHD], dv[kHD];
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) {
+    k[d] = ok ? p.k[(long long)b * p.kbs + (long long)j * p.ldk + h * kHD + d] : 0.f;
+    v[d] = ok ? p.v[(long long)b * p.vbs + (long long)j * p.ldv + h * kHD + d] : 0.f;
+    dk[d] = 0.f; dv[d] = 0.f;
+  }
+  for (int i0 = 0; i0 < p.Lq; i0 += kBwdTile) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kBwdTile * kHD; e += kBwdRows) {
+      const int r = e / kHD, d = e % kHD, i = i0 + r;
+      sq[r][d] = i < p.Lq ? p.q[(long long)b * p.qbs + (long long)i * p.ldq + h * kHD + d] * p.scale : 0.f;
+      sg[r][d] = i < p.Lq ? p.dout[(long long)b * p.dbs + (long long)i * p.ldd + h * kHD + d] : 0.f;
+    }
+    if (threadIdx.x < kBwdTile) {
+      const int i = i0 + threadIdx.x;
+      const long long row = ((long long)b * p.heads + h) * p.Lq + i;
+      s_lse[threadIdx.x] = i < p.Lq ? p.lse[row] : INFINITY;          // exp(s - inf) = 0: padding rows contribute nothing
+      s_delta[threadIdx.x] = i < p.Lq ? p.delta[row] : 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < kBwdTile; ++r) {
+      float sc = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < kHD; ++d) { sc = fmaf(sq[r][d], k[d], sc); dp = fmaf(sg[r][d], v[d], dp); }
+      const float pij = expf(sc - s_lse[r]);
+      const float ds = pij * (dp - s_delta[r]);
+#pragma unroll
+      for (int d = 0; d < kHD; ++d) { dv[d] = fmaf(pij, sg[r][d], dv[d]); dk[d] = fmaf(ds, sq[r][d], dk[d]); }   // sq already holds scale * q
+    }
+  }
+  if (!ok) return;
+#pragma unroll
+  for (int d = 0; d < kHD; ++d) {
+    p.dk[((long long)b * p.Lk + j) * (p.heads * kHD) + h * kHD + d] = dk[d];
+    p.dv[((long long)b * p.Lk + j) * (p.heads * kHD) + h * kHD + d] = dv[d];
+  }
+}
+
+// TC_PW_* modes (include/transcar_b200.h)
+__global__ void pointwise_kernel(const float* __restrict__ grad, const float* __restrict__ x, float* __restrict__ out, int n,
+                                 int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float xv = x[i];
+  if (mode == TC_PW_LOGIT) { out[i] = logit_f32(xv); return; }
+  if (mode == TC_PW_SIGMOID) { out[i] = sigmoid_f32(xv); return; }
+  const float g = grad[i];
+  if (mode == TC_PW_SIGMOID_BWD) { out[i] = g * xv * (1.0f - xv); return; }
+  const float eps = 1e-5f;
+  float d = 0.f;
+  if (xv >= 0.f && xv <= 1.f) {
+    const float a = fmaxf(xv, eps), bq = fmaxf(1.0f - xv, eps);
+    if (xv >= eps) d += 1.0f / a;
+    if (1.0f - xv >= eps) d += 1.0f / bq;
+  }
+  out[i] = g * d;
+}
+
+__global__ void add_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n4,
+                                int N4, int period) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const long long m = i / N4;
+  const int c = (int)(i % N4);
+  const float4 x = reinterpret_cast<const float4*>(a)[i];
+  const float4 y = reinterpret_cast<const float4*>(b)[(m % period) * N4 + c];
+  reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+}
+
+__global__ void period_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int batches, long long pn) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pn) return;
+  float s = 0.f;
+  for (int b = 0; b < batches; ++b) s += x[(long long)b * pn + i];
+  out[i] += s;
+}
+
+}  // namespace
+}  // namespace tc
+
+extern "C" int tc_attention_dense_bwd(const tc_attention_dense_bwd_args* a, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(a != nullptr, TC_ERR_NULL, "tc_attention_dense_bwd: args is NULL");
+  TC_REQUIRE(a->q && a->k && a->v && a->o && a->dout && a->dq && a->dk && a->dv && a->workspace, TC_ERR_NULL,
+             "tc_attention_dense_bwd: NULL pointer");
+  TC_REQUIRE(a->D == 32, TC_ERR_SHAPE, "tc_attention_dense_bwd: head dim must be 32 (got %d)", a->D);
+  TC_REQUIRE(a->B >= 0 && a->Lq >= 0 && a->Lk > 0 && a->heads > 0 && a->B <= 65535 && a->heads <= 65535, TC_ERR_SHAPE,
+             "tc_attention_dense_bwd: bad shape");
+  if (a->B == 0 || a->Lq == 0) return TC_OK;
+  DenseBwdParams p{a->q, a->k, a->v, a->o, a->dout, a->ldq, a->ldk, a->ldv, a->ldo, a->ld_dout,
+                   a->q_batch_stride, a->k_batch_stride, a->v_batch_stride, a->o_batch_stride, a->dout_batch_stride,
+                   a->B, a->Lq, a->Lk, a->heads, a->scale, a->dq, a->dk, a->dv,
+                   a->workspace, a->workspace + (long long)a->B * a->heads * a->Lq};
+  cudaStream_t s = as_stream(stream);
+  attn_dense_bwd_dq_kernel<<<dim3((a->Lq + kBwdRows - 1) / kBwdRows, a->heads, a->B), kBwdRows, 0, s>>>(p);
+  attn_dense_bwd_dkv_kernel<<<dim3((a->Lk + kBwdRows - 1) / kBwdRows, a->heads, a->B), kBwdRows, 0, s>>>(p);
+  count_launch(2);
+  return check_launch("tc_attention_dense_bwd");
+}
+
+extern "C" int tc_pointwise(const float* grad, const float* x, float* out, int32_t n, int32_t mode, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(x && out, TC_ERR_NULL, "tc_pointwise: NULL pointer");
+  TC_REQUIRE(n >= 0 && mode >= TC_PW_LOGIT_BWD && mode <= TC_PW_SIGMOID, TC_ERR_SHAPE, "tc_pointwise: bad n / mode");
+  TC_REQUIRE(grad || mode >= TC_PW_LOGIT, TC_ERR_NULL, "tc_pointwise: backward modes need grad");
+  if (n == 0) return TC_OK;
+  pointwise_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(grad, x, out, n, mode);
+  count_launch();
+  return check_launch("tc_pointwise");
+}
+
+extern "C" int tc_add_rows(const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t period, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(a && b && out, TC_ERR_NULL, "tc_add_rows: NULL pointer");
+  TC_REQUIRE(M >= 0 && N > 0 && N % 4 == 0 && period > 0, TC_ERR_SHAPE, "tc_add_rows: bad shape (N must be a multiple of 4)");
+  TC_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), TC_ERR_ALIGN, "tc_add_rows: pointers must be 16-byte aligned");
+  if (M == 0) return TC_OK;
+  const long long n4 = (long long)M * (N / 4);
+  add_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(a, b, out, n4, N / 4, period);
+  count_launch();
+  return check_launch("tc_add_rows");
+}
+
+extern "C" int tc_period_sum(const float* x, float* out, int32_t batches, int32_t period, int32_t N, tc_stream_t stream) {
+  using namespace tc;
+  TC_REQUIRE(x && out, TC_ERR_NULL, "tc_period_sum: NULL pointer");
+  TC_REQUIRE(batches >= 0 && period >= 0 && N > 0, TC_ERR_SHAPE, "tc_period_sum: bad shape");
+  const long long pn = (long long)period * N;
+  if (batches == 0 || pn == 0) return TC_OK;
+  period_sum_kernel<<<(unsigned)((pn + 255) / 256), 256, 0, as_stream(stream)>>>(x, out, batches, pn);
+  count_launch();
+  return check_launch("tc_period_sum");
+}
+
 extern "C" int tc_transpose(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst,
                             int32_t rows, int32_t cols, tc_stream_t stream) {
   using namespace tc;

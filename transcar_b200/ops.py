@@ -535,3 +535,122 @@ def attention_sparse_bwd(q, k, v, dout, heads, geom, key_xy, dk, dv, scale=None)
     a.ld_dk, a.ld_dv, a.dk_batch_stride, a.dv_batch_stride = dk.stride(1), dv.stride(1), dk.stride(0), dv.stride(0)
     _lib.check(_call("attention_sparse_bwd", lib.tc_attention_sparse_bwd, C.byref(a), _stream()), "attention_sparse_bwd")
     return dq
+
+
+def sample_bwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, dout, want_feat_grad=False, d_feats=None,
+               want_logit_grad=True, want_ref_grad=False):
+    """Backward of :func:`sample_fwd` (``tc_sample_bwd``).  ``dout`` [B,Q,C] fp32.  Returns
+    ``(d_feats or None, d_logits [B,Q,N*L] or None, d_ref [B,Q,3] or None)``; ``d_feats`` are fp32 channels-last maps that
+    are ACCUMULATED into (pass existing ones through ``d_feats`` or let ``want_feat_grad`` allocate zeroed ones)."""
+    lib = _lib.load()
+    a = _lib.SampleBwdArgs()
+    B, N, Cc = feats[0].shape[:3]
+    Q = ref.shape[1]
+    if len(feats) != 4:
+        raise RuntimeError("transcar_b200.sample_bwd: exactly 4 feature levels are supported")
+    if want_feat_grad and d_feats is None:
+        d_feats = [torch.zeros((B, N, f.shape[3], f.shape[4], Cc), device=f.device, dtype=torch.float32).permute(0, 1, 4, 2, 3)
+                   for f in feats]
+    for l, f in enumerate(feats):
+        _need(f, f"feats[{l}]", last_contig=False)
+        if not is_channels_last_5d(f):
+            raise RuntimeError(f"transcar_b200.sample_bwd: feats[{l}] is not channels-last")
+        a.feat[l] = f.data_ptr()
+        a.H[l], a.W[l] = f.shape[3], f.shape[4]
+        if d_feats is not None:
+            g = _need(d_feats[l], f"d_feats[{l}]", torch.float32, last_contig=False)
+            if not is_channels_last_5d(g) or g.shape != f.shape:
+                raise RuntimeError(f"transcar_b200.sample_bwd: d_feats[{l}] must be a channels-last fp32 map shaped like feats[{l}]")
+            a.d_feat[l] = g.data_ptr()
+    ref = _need(ref, "ref", torch.float32).contiguous()
+    lidar2img = _need(lidar2img, "lidar2img", torch.float32).contiguous()
+    attn_logits = _need(attn_logits, "attn_logits", torch.float32).contiguous()
+    dout = _need(dout, "dout", torch.float32).contiguous()
+    assert ref.shape == (B, Q, 3) and attn_logits.shape == (B, Q, N * 4) and dout.shape == (B, Q, Cc)
+    a.num_levels, a.B, a.N, a.Q, a.C = 4, B, N, Q, Cc
+    a.feat_dtype = _DT[feats[0].dtype]
+    a.ref, a.lidar2img, a.attn_logits, a.dout = ref.data_ptr(), lidar2img.data_ptr(), attn_logits.data_ptr(), dout.data_ptr()
+    for i in range(6):
+        a.pc_range[i] = float(pc_range[i])
+    a.img_w, a.img_h = float(img_w), float(img_h)
+    d_logits = torch.empty((B, Q, N * 4), device=ref.device, dtype=torch.float32) if want_logit_grad else None
+    d_ref = torch.empty((B, Q, 3), device=ref.device, dtype=torch.float32) if want_ref_grad else None
+    a.d_logits, a.d_ref = _ptr(d_logits), _ptr(d_ref)
+    _lib.check(_call("sample_bwd", lib.tc_sample_bwd, C.byref(a), _stream()), "sample_bwd")
+    return d_feats, d_logits, d_ref
+
+
+def attention_dense_bwd(q, k, v, o, dout, heads, scale=None):
+    """Backward of the mask-free attention core (fp32): q/o/dout [B,Lq,E], k/v [B,Lk,E] (strided views are fine) ->
+    (dq [B,Lq,E], dk [B,Lk,E], dv [B,Lk,E]) contiguous."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
+        _need(t, n, torch.float32)
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    D = E // heads
+    dq = torch.empty((B, Lq, E), device=q.device, dtype=torch.float32)
+    dk = torch.empty((B, Lk, E), device=q.device, dtype=torch.float32)
+    dv = torch.empty((B, Lk, E), device=q.device, dtype=torch.float32)
+    ws = torch.empty((2, B, heads, Lq), device=q.device, dtype=torch.float32)
+    a = _lib.AttentionDenseBwdArgs()
+    a.q, a.k, a.v, a.o, a.dout = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ldo, a.ld_dout = q.stride(1), k.stride(1), v.stride(1), o.stride(1), dout.stride(1)
+    a.q_batch_stride, a.k_batch_stride, a.v_batch_stride = q.stride(0), k.stride(0), v.stride(0)
+    a.o_batch_stride, a.dout_batch_stride = o.stride(0), dout.stride(0)
+    a.B, a.Lq, a.Lk, a.heads, a.D = B, Lq, Lk, heads, D
+    a.scale = float(scale if scale is not None else 1.0 / math.sqrt(D))
+    a.dq, a.dk, a.dv, a.workspace = dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr()
+    _lib.check(_call("attention_dense_bwd", lib.tc_attention_dense_bwd, C.byref(a), _stream()), "attention_dense_bwd")
+    return dq, dk, dv
+
+
+def _pointwise(grad, x, mode, what):
+    lib = _lib.load()
+    x = _need(x, "x", torch.float32).contiguous()
+    if grad is not None:
+        grad = _need(grad, "grad", torch.float32).contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_call(what, lib.tc_pointwise, _ptr(grad), _ptr(x), _ptr(out), x.numel(), mode, _stream()), what)
+    return out
+
+
+def logit_bwd(grad, x):
+    """d/dx of inverse_sigmoid (T:17-32) applied to an upstream gradient."""
+    return _pointwise(grad, x, 0, "logit_bwd")
+
+
+def sigmoid_bwd(grad, y):
+    """grad * y * (1 - y) for y = sigmoid(.)."""
+    return _pointwise(grad, y, 1, "sigmoid_bwd")
+
+
+def logit(x):
+    """inverse_sigmoid (T:17-32)."""
+    return _pointwise(None, x, 2, "logit")
+
+
+def sigmoid(x):
+    return _pointwise(None, x, 3, "sigmoid")
+
+
+def add_rows(a, b, period=None, out=None):
+    """out[m,:] = a[m,:] + b[m % period,:] for contiguous fp32 [M,N] / [period,N] (``out`` may be ``a``)."""
+    lib = _lib.load()
+    a = _need(a, "a", torch.float32)
+    b = _need(b, "b", torch.float32)
+    assert a.is_contiguous() and b.is_contiguous() and a.dim() == 2 and b.shape[1] == a.shape[1]
+    period = period or b.shape[0]
+    out = torch.empty_like(a) if out is None else out
+    _lib.check(_call("add_rows", lib.tc_add_rows, _ptr(a), _ptr(b), _ptr(out), a.shape[0], a.shape[1], period, _stream()), "add_rows")
+    return out
+
+
+def period_sum_(x, out):
+    """out[r,:] += sum_b x[b*period + r,:]; x [B*period, N], out [period, N] fp32 contiguous."""
+    lib = _lib.load()
+    x, out = _need(x, "x", torch.float32), _need(out, "out", torch.float32)
+    assert x.is_contiguous() and out.is_contiguous() and x.shape[1] == out.shape[1] and x.shape[0] % out.shape[0] == 0
+    _lib.check(_call("period_sum", lib.tc_period_sum, _ptr(x), _ptr(out), x.shape[0] // out.shape[0], out.shape[0], out.shape[1],
+                     _stream()), "period_sum")
+    return out

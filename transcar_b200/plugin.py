@@ -526,8 +526,6 @@ class Detr3DHead(nn.Module):
             self._engine_key = key
         return self._engine
 
-    _FROZEN = ("transformer.", "cls_branches.", "reg_branches.", "query_embedding.")
-
     def decoder_engine(self):
         """Decoder-only engine for the training variant, keyed on the tensors it actually consumes (the frozen DETR3D
         transformer, ``reg_branches`` and the query embedding): optimizer steps on the radar head do not rebuild it."""
@@ -558,16 +556,38 @@ class Detr3DHead(nn.Module):
         return self.engine().forward(mlvl_feats, img_metas, return_aux=return_aux)
 
     def forward_train(self, mlvl_feats, img_metas):
-        """Training variant (reference recipe ``tools/train.py:238-252``: only the radar head trains).  The frozen DETR3D
-        decoder runs through the inference engine without autograd; the radar head runs through
-        ``transcar_b200.training.RadarHeadTrainer`` (library kernels forward and backward) behind one autograd node, so
-        ``loss.backward()`` fills ``.grad`` of the radar-head parameters.  Dropout (p = 0.1 in the reference configs) is
-        not applied.  Parameters outside the radar head receive no gradient."""
-        from .training import RadarHeadTrainer, radar_head_apply
-        if any(p.requires_grad for n, p in self.named_parameters() if n.startswith(self._FROZEN)):
-            raise NotImplementedError(
-                "transcar_b200: only the radar head trains (reference recipe, tools/train.py:238-252); freeze "
-                "transformer.*, cls_branches.*, reg_branches.* and query_embedding.* (requires_grad_(False))")
+        """Training variant.  Reference recipe (``tools/train.py:238-252``): only the radar head trains - the frozen DETR3D
+        decoder runs through the inference engine without autograd and the radar head through
+        ``transcar_b200.training.RadarHeadTrainer`` (library kernels forward and backward) behind one autograd node.
+        Un-frozen recipe (any ``transformer.*`` / ``query_embedding`` parameter requires grad): the decoder runs through
+        ``DecoderTrainer`` as well - sampling backward (grid_sample scatter), dense attention backward, Linear / LayerNorm
+        tape - and the feature maps receive a gradient when they require one.  ``cls_branches`` / ``reg_branches`` have no
+        gradient path in TransCAR (detached reference points, thresholded masks) and keep ``.grad = None``.
+        Dropout (p = 0.1 in the reference configs) is not applied: the module raises when asked to (``train_dropout``)."""
+        from .training import DecoderTrainer, RadarHeadTrainer, fusion_head_apply, radar_head_apply
+        named = dict(self.named_parameters())
+        unfrozen = any(p.requires_grad for n, p in named.items() if n.startswith(("transformer.", "query_embedding.")))
+        key = tuple(p.data_ptr() for p in named.values())
+        if getattr(self, "_trainer", None) is None or self._trainer_key != key:
+            live = {k: v.data for k, v in named.items() if v.dtype == torch.float32}
+            tc = self.precision != "fp32"
+            self._trainer = RadarHeadTrainer(live, num_heads=8, pc_range=self.pc_range, tensor_cores=tc)
+            layer0 = self.transformer.decoder.layers[0]
+            self._dec_trainer = DecoderTrainer(live, self.num_query, num_heads=layer0.attentions[0].num_heads,
+                                               num_layers=self.transformer.decoder.num_layers, pc_range=self.pc_range,
+                                               tensor_cores=tc)
+            self._trainer_key = key
+        if unfrozen:
+            eng = self.decoder_engine()                  # host-side input staging only (layout hand-off, metas, radar tokens)
+            with torch.no_grad():
+                feats, l2i, img_w, img_h, tokens, key_xy = eng.prepare_inputs(
+                    [f.detach() for f in mlvl_feats], img_metas, radar=True)
+            B = feats[0].shape[0]
+            # gradients flow to the caller's feature tensors only when they already are in the kernels' layout (zero-copy)
+            live_feats = [m if (m.requires_grad and m.data_ptr() == f.data_ptr()) else f for m, f in zip(mlvl_feats, feats)]
+            cls_all, reg_all = fusion_head_apply(self._dec_trainer, self._trainer, named, live_feats, l2i, img_w, img_h,
+                                                 tokens, key_xy, B)
+            return dict(all_cls_scores=cls_all, all_bbox_preds=reg_all, enc_cls_scores=None, enc_bbox_preds=None)
         eng = self.decoder_engine()
         with torch.no_grad():
             feats, l2i, img_w, img_h, tokens, key_xy = eng.prepare_inputs(mlvl_feats, img_metas, radar=True)
@@ -576,13 +596,6 @@ class Detr3DHead(nn.Module):
             # decoder() joins its side branch before returning: ref / code are safe to read on this stream
             _, _, x32, _, ref, code = eng.decoder(feats, l2i, img_w, img_h, B, keep_all=False)
             eng._keep = []
-        named = dict(self.named_parameters())
-        key = tuple(p.data_ptr() for p in named.values())
-        if getattr(self, "_trainer", None) is None or self._trainer_key != key:
-            live = {k: v.data for k, v in named.items() if v.dtype == torch.float32}
-            self._trainer = RadarHeadTrainer(live, num_heads=8, pc_range=self.pc_range,
-                                             tensor_cores=self.precision != "fp32")
-            self._trainer_key = key
         cls_all, reg_all = radar_head_apply(self._trainer, named, x32.float(), ref, code, tokens, key_xy, B)
         return dict(all_cls_scores=cls_all, all_bbox_preds=reg_all, enc_cls_scores=None, enc_bbox_preds=None)
 

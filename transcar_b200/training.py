@@ -43,17 +43,24 @@ def trainable_names(state_dict_keys):
     return [k for k in state_dict_keys if k.startswith(pre)]
 
 
-class RadarHeadTrainer:
-    """fp32 forward/backward of the radar fusion head over batch-major ``[B*Q, C]`` activations."""
+def decoder_trainable_names(state_dict_keys):
+    """Parameters with a gradient path when the DETR3D decoder is NOT frozen: the six decoder layers, the reference-point
+    Linear and the query embedding.  ``cls_branches`` / ``reg_branches`` stay without gradient in TransCAR: their outputs
+    reach the loss only through detached reference points (T:203) and the thresholded radar mask (H:543-571)."""
+    return [k for k in state_dict_keys if k.startswith("transformer.") or k == "query_embedding.weight"]
 
-    def __init__(self, params, num_heads=8, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), tensor_cores=True):
-        """``params``: dict name -> fp32 CUDA tensor (the live parameters, reference key names)."""
+
+class _TapeOps:
+    """Taped Linear / LayerNorm building blocks shared by the radar-head and the decoder trainers: parameters by reference
+    key name in ``self.p``, gradients accumulated into views of one flat buffer (``self.g``)."""
+
+    def _setup(self, params, names, num_heads, pc_range, tensor_cores):
         self.p = params
         self.tc = tensor_cores
         self._wcache = {}                   # split-bf16 copies of the weights, valid for one forward / backward
         self.heads = num_heads
         self.pc_range = [float(v) for v in pc_range]
-        self.names = trainable_names(params.keys())
+        self.names = names
         dev = next(iter(params.values())).device
         n = sum(params[k].numel() for k in self.names)
         self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -75,16 +82,17 @@ class RadarHeadTrainer:
         return t
 
     # ------------------------------------------------------------------ differentiable pieces (forward records a tape)
-    def _linear(self, tape, x, wkey, bkey, relu=False, residual=None, gate=None, w_rows=None):
-        """y = [relu]( gate * (x W^T + b) + residual ).  ``w_rows`` selects a row range of a packed weight/bias."""
+    def _linear(self, tape, x, wkey, bkey, relu=False, residual=None, gate=None, w_rows=None, residual2=None):
+        """y = [relu]( gate * (x W^T + b) + residual + residual2 ).  ``w_rows`` selects a row range of a packed
+        weight/bias.  The residual terms pass their gradient through unchanged (the caller routes it)."""
         W, b = self.p[wkey], self.p[bkey]
         if w_rows is not None:
             W, b = W[w_rows[0]:w_rows[1]], b[w_rows[0]:w_rows[1]]
         if self.tc and x.shape[1] % 64 == 0:
             y, _ = ops.linear(ops.cast_split(x), self._wsplit(wkey, w_rows, W, False), b, relu=relu, residual=residual,
-                              row_gate=gate)
-        else:               # K = 3 / 36 (raw radar fields): exact fp32 CUDA-core path
-            y, _ = ops.linear(x, W, b, relu=relu, residual=residual, row_gate=gate)
+                              residual2=residual2, row_gate=gate)
+        else:               # K = 3 / 36 (raw radar fields, reference points): exact fp32 CUDA-core path
+            y, _ = ops.linear(x, W, b, relu=relu, residual=residual, residual2=residual2, row_gate=gate)
         tape.append(("linear", x, wkey, bkey, w_rows, y if relu else None, gate))
         return y
 
@@ -121,6 +129,14 @@ class RadarHeadTrainer:
             dy = ops.mask_grad(dy, y=y_relu)
         return ops.layernorm_bwd(dy, x, mean, rstd, self.p[key + ".weight"], dgamma=self.g[key + ".weight"],
                                  dbeta=self.g[key + ".bias"], add=add)
+
+
+class RadarHeadTrainer(_TapeOps):
+    """Forward / backward of the radar fusion head over batch-major ``[B*Q, C]`` activations."""
+
+    def __init__(self, params, num_heads=8, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), tensor_cores=True):
+        """``params``: dict name -> fp32 CUDA tensor (the live parameters, reference key names)."""
+        self._setup(params, trainable_names(params.keys()), num_heads, pc_range, tensor_cores)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x0, ref, code, tokens, key_xy, B):
@@ -195,8 +211,9 @@ class RadarHeadTrainer:
         return cls_all, reg_all
 
     # ------------------------------------------------------------------ backward
-    def backward(self, d_cls, d_reg):
-        """d_cls / d_reg: [3,B,Q,10] upstream gradients.  Accumulates into ``self.flat_grad`` (zero it per step)."""
+    def backward(self, d_cls, d_reg, need_dx0=False):
+        """d_cls / d_reg: [3,B,Q,10] upstream gradients.  Accumulates into ``self.flat_grad`` (zero it per step).
+        ``need_dx0``: also return the gradient w.r.t. the decoder output ``x0`` (un-frozen decoder)."""
         ctx = self.ctx
         B, Q, R, C = ctx["B"], ctx["Q"], ctx["R"], ctx["C"]
         M = B * Q
@@ -231,7 +248,7 @@ class RadarHeadTrainer:
             dq = ops.attention_sparse_bwd(L["q"].view(B, Q, C), kv3[:, :, :C], kv3[:, :, C:], datt.view(B, Q, C), self.heads,
                                           L["geom"], ctx["key_xy"], dkv[:, :, :C], dkv[:, :, C:])
             d_kvfeat = self._linear_bwd(tape[1], dkv.view(B * R, 2 * C), dx_accum=d_kvfeat)
-            dx_next = self._linear_bwd(tape[0], dq.view(M, C), dx_accum=dz2, need_dx=li > 0)   # + skip z2 = x + ...
+            dx_next = self._linear_bwd(tape[0], dq.view(M, C), dx_accum=dz2, need_dx=li > 0 or need_dx0)   # + skip z2 = x + ...
         # ---- radar encoders: kvfeat = pos + relu(feat)
         enc, n_pos = ctx["enc"], ctx["n_pos"]
         df = self._linear_bwd(enc[n_pos + 2], d_kvfeat)
@@ -243,7 +260,148 @@ class RadarHeadTrainer:
         self._linear_bwd(enc[0], dp, need_dx=False)
         self.ctx = None
         self._wcache = {}
+        self.dx0 = dx_next if need_dx0 else None
         return self.g
+
+
+class DecoderTrainer(_TapeOps):
+    """Forward / backward of the six DETR3D decoder layers (T:155-214 + the mmcv layer of cfg
+    ``detr3d_res101_gridmask.py:65-82``) for the un-frozen recipe: everything BASELINE.json configs[4] names - the
+    grid_sample scatter (``tc_sample_bwd``) and the dense self-attention backward (``tc_attention_dense_bwd``) - plus the
+    Linear / LayerNorm tape shared with the radar head.  Reference points are detached between layers (T:203), so only layer 0
+    sends gradient into ``transformer.reference_points`` (through the sampling grid and the position encoder); the
+    refinement branches themselves run without a tape.  Dropout is not applied (identity in eval; see ``forward_train``)."""
+
+    def __init__(self, params, num_query, num_heads=8, num_layers=6, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0),
+                 tensor_cores=True):
+        self._setup(params, decoder_trainable_names(params.keys()), num_heads, pc_range, tensor_cores)
+        self.Q, self.L = num_query, num_layers
+
+    def _reg_branch(self, l, x):
+        """reg_branches[l] without a tape: its output only feeds detached reference points and the radar-mask thresholds."""
+        p = self.p
+        h, _ = ops.linear(x, p[f"reg_branches.{l}.0.weight"], p[f"reg_branches.{l}.0.bias"], relu=True)
+        h, _ = ops.linear(h, p[f"reg_branches.{l}.2.weight"], p[f"reg_branches.{l}.2.bias"], relu=True)
+        return ops.linear(h, p[f"reg_branches.{l}.4.weight"], p[f"reg_branches.{l}.4.bias"])[0]
+
+    def forward(self, feats, l2i, img_w, img_h, B):
+        """feats: 4 channels-last maps; returns (x [B*Q,C], ref [B*Q,3], code [B*Q,10]) = decoder output, refined reference
+        points, ``reg_branches[5]`` output - what the radar head consumes."""
+        Q, L = self.Q, self.L
+        emb = self.p["query_embedding.weight"]
+        C = emb.shape[1] // 2
+        M = B * Q
+        self._wcache = {}
+        pos_q = emb[:, :C].contiguous()                                  # T:119-121
+        x = emb[:, C:].contiguous().unsqueeze(0).expand(B, Q, C).reshape(M, C).contiguous()
+        head = []
+        r0 = self._linear(head, pos_q, "transformer.reference_points.weight", "transformer.reference_points.bias")
+        ref_q = ops.sigmoid(r0)                                          # T:122-123  [Q,3]
+        ref = ref_q.unsqueeze(0).expand(B, Q, 3).reshape(M, 3).contiguous()
+        ctx = dict(B=B, Q=Q, C=C, head=head, ref_q=ref_q, ref0=ref, layers=[], feats=feats, l2i=l2i, img=(img_w, img_h))
+        code = None
+        for l in range(L):
+            pre = f"transformer.decoder.layers.{l}."
+            mha, ca = pre + "attentions.0.attn.", pre + "attentions.1."
+            tape = []
+            # ---- self-attention: q = k = x + query_pos, v = x (mmcv MultiheadAttention wrapper)
+            xp = ops.add_rows(x, pos_q, Q)
+            q = self._linear(tape, xp, mha + "in_proj_weight", mha + "in_proj_bias", w_rows=(0, C))
+            k = self._linear(tape, xp, mha + "in_proj_weight", mha + "in_proj_bias", w_rows=(C, 2 * C))
+            v = self._linear(tape, x, mha + "in_proj_weight", mha + "in_proj_bias", w_rows=(2 * C, 3 * C))
+            o, _ = ops.attention(q.view(B, Q, C), k.view(B, Q, C), v.view(B, Q, C), self.heads, algo="simt")
+            z = self._linear(tape, o.view(M, C), mha + "out_proj.weight", mha + "out_proj.bias", residual=x)
+            x1 = self._ln(tape, z, pre + "norms.0")
+            # ---- Detr3DCrossAtten (T:302-378): residual = x1 (quirk Q1), logits from x1 + query_pos
+            xp1 = ops.add_rows(x1, pos_q, Q)
+            logits = self._linear(tape, xp1, ca + "attention_weights.weight", ca + "attention_weights.bias")
+            s, _ = ops.sample_fwd(feats, ref.view(B, Q, 3), l2i, logits.view(B, Q, -1), self.pc_range, img_w, img_h)
+            lg = ops.logit(ref)
+            pe = self._ln(tape, self._linear(tape, lg, ca + "position_encoder.0.weight", ca + "position_encoder.0.bias"),
+                          ca + "position_encoder.1", relu=True)
+            pf = self._ln(tape, self._linear(tape, pe, ca + "position_encoder.3.weight", ca + "position_encoder.3.bias"),
+                          ca + "position_encoder.4", relu=True)
+            z2 = self._linear(tape, s.view(M, C), ca + "output_proj.weight", ca + "output_proj.bias", residual=x1, residual2=pf)
+            x2 = self._ln(tape, z2, pre + "norms.1")
+            # ---- FFN
+            h = self._linear(tape, x2, pre + "ffns.0.layers.0.0.weight", pre + "ffns.0.layers.0.0.bias", relu=True)
+            z3 = self._linear(tape, h, pre + "ffns.0.layers.1.weight", pre + "ffns.0.layers.1.bias", residual=x2)
+            x3 = self._ln(tape, z3, pre + "norms.2")
+            ctx["layers"].append(dict(tape=tape, q=q, k=k, v=v, o=o, ref=ref, logits=logits))
+            # ---- iterative refinement (T:190-203), detached
+            code = self._reg_branch(l, x3)
+            ref = ops.ref_update(code, ref)
+            x = x3
+        self.ctx = ctx
+        return x, ref, code
+
+    def backward(self, dx, want_feat_grad=False):
+        """dx [B*Q,C]: gradient w.r.t. the decoder output.  Accumulates parameter gradients into ``self.flat_grad``;
+        returns the feature-map gradients (4 fp32 channels-last maps) when ``want_feat_grad``."""
+        ctx = self.ctx
+        B, Q, C = ctx["B"], ctx["Q"], ctx["C"]
+        M = B * Q
+        feats, l2i, (img_w, img_h) = ctx["feats"], ctx["l2i"], ctx["img"]
+        dev = dx.device
+        dpos = torch.zeros((M, C), device=dev, dtype=torch.float32)      # gradient of the batch-broadcast query_pos
+        d_feats = None
+        d_ref0 = None
+        for l in range(self.L - 1, -1, -1):
+            Lc = ctx["layers"][l]
+            t = Lc["tape"]
+            # tape order: 0 q, 1 k, 2 v, 3 out_proj, 4 norms.0, 5 attention_weights, 6 pe.0, 7 pe.1, 8 pe.3, 9 pe.4,
+            #             10 output_proj, 11 norms.1, 12 ffn1, 13 ffn2, 14 norms.2
+            dz3 = self._ln_bwd(t[14], dx)
+            dh = self._linear_bwd(t[13], dz3)
+            dx2 = self._linear_bwd(t[12], dh, dx_accum=dz3)
+            dz2 = self._ln_bwd(t[11], dx2)                                # = d x1 (residual) = d pos_feat (residual2)
+            ds = self._linear_bwd(t[10], dz2)
+            # position encoder (T:377): gradient reaches the reference points only in layer 0
+            dpe = self._ln_bwd(t[9], dz2)
+            dpe = self._linear_bwd(t[8], dpe)
+            dpe = self._ln_bwd(t[7], dpe)
+            d_lg = self._linear_bwd(t[6], dpe, need_dx=l == 0)
+            # sampling (T:367-373, 381-422)
+            d_feats, d_logits, d_ref_s = ops.sample_bwd(feats, Lc["ref"].view(B, Q, 3), l2i, Lc["logits"].view(B, Q, -1),
+                                                        self.pc_range, img_w, img_h, ds.view(B, Q, C),
+                                                        want_feat_grad=want_feat_grad, d_feats=d_feats, want_ref_grad=l == 0)
+            dxp1 = self._linear_bwd(t[5], d_logits.view(M, -1))
+            ops.add_rows(dpos, dxp1, M, out=dpos)
+            dx1 = ops.add_rows(dz2, dxp1, M)
+            if l == 0:
+                d_ref0 = ops.add_rows(_pad4(d_ref_s.view(M, 3)), _pad4(ops.logit_bwd(d_lg, Lc["ref"])), M)[:, :3]
+            # self-attention
+            dz = self._ln_bwd(t[4], dx1)
+            do = self._linear_bwd(t[3], dz)
+            dq, dk, dv = ops.attention_dense_bwd(Lc["q"].view(B, Q, C), Lc["k"].view(B, Q, C), Lc["v"].view(B, Q, C), Lc["o"],
+                                                 do.view(B, Q, C), self.heads)
+            dxp = self._linear_bwd(t[0], dq.view(M, C))
+            dxp = self._linear_bwd(t[1], dk.view(M, C), dx_accum=dxp)
+            ops.add_rows(dpos, dxp, M, out=dpos)
+            dxv = self._linear_bwd(t[2], dv.view(M, C), dx_accum=dz)      # + residual z = x + ...
+            dx = ops.add_rows(dxv, dxp, M)
+        # ---- query embedding (T:119-121) and the initial reference points (T:122-123)
+        g_emb = self.g["query_embedding.weight"]
+        d_query = torch.zeros((Q, C), device=dev, dtype=torch.float32)
+        d_posq = torch.zeros((Q, C), device=dev, dtype=torch.float32)
+        ops.period_sum_(dx, d_query)
+        ops.period_sum_(dpos, d_posq)
+        d_refq = torch.zeros((Q, 4), device=dev, dtype=torch.float32)
+        ops.period_sum_(_pad4(d_ref0), d_refq)
+        d_r0 = ops.sigmoid_bwd(d_refq[:, :3].contiguous(), ctx["ref_q"])
+        d_posq = self._linear_bwd(ctx["head"][0], d_r0, dx_accum=d_posq)
+        g_emb[:, :C] += d_posq
+        g_emb[:, C:] += d_query
+        self.ctx = None
+        self._wcache = {}
+        return d_feats
+
+
+def _pad4(t):
+    """[M,3] -> contiguous [M,4] (zero column): the row kernels work on 16-byte rows."""
+    out = torch.zeros((t.shape[0], 4), device=t.device, dtype=t.dtype)
+    out[:, :3] = t
+    return out
 
 
 class _RadarHeadFunction(torch.autograd.Function):
@@ -265,6 +423,38 @@ class _RadarHeadFunction(torch.autograd.Function):
             tr.flat_grad.zero_()
             grads = tr.backward(d_cls.contiguous(), d_reg.contiguous())
         return (None,) * 7 + tuple(grads[k].clone() for k in tr.names)
+
+
+class _FusionHeadFunction(torch.autograd.Function):
+    """Autograd bridge of the un-frozen recipe: decoder tape + radar-head tape behind one node.  Inputs: the four feature
+    maps (gradient only when they require it), then the decoder parameters, then the radar-head parameters."""
+
+    @staticmethod
+    def forward(ctx, dec, radar, l2i, img_w, img_h, tokens, key_xy, B, *tensors):
+        feats = list(tensors[:4])
+        ctx.dec, ctx.radar = dec, radar
+        ctx.feat_grad = [f.requires_grad for f in feats]
+        ctx.feat_dtype = feats[0].dtype
+        with torch.no_grad():
+            x0, ref, code = dec.forward([f.detach() for f in feats], l2i, img_w, img_h, B)
+            cls_all, reg_all = radar.forward(x0, ref, code, tokens, key_xy, B)
+        return cls_all, reg_all
+
+    @staticmethod
+    def backward(ctx, d_cls, d_reg):
+        dec, radar = ctx.dec, ctx.radar
+        with torch.no_grad():
+            radar.flat_grad.zero_()
+            dec.flat_grad.zero_()
+            rg = radar.backward(d_cls.contiguous(), d_reg.contiguous(), need_dx0=True)
+            d_feats = dec.backward(radar.dx0, want_feat_grad=any(ctx.feat_grad))
+        fg = [(g.to(ctx.feat_dtype) if (w and g is not None) else None) for w, g in zip(ctx.feat_grad, d_feats or [None] * 4)]
+        return (None,) * 8 + tuple(fg) + tuple(dec.g[k].clone() for k in dec.names) + tuple(rg[k].clone() for k in radar.names)
+
+
+def fusion_head_apply(dec, radar, named_params, feats, l2i, img_w, img_h, tokens, key_xy, B):
+    plist = [named_params[k] for k in dec.names] + [named_params[k] for k in radar.names]
+    return _FusionHeadFunction.apply(dec, radar, l2i, img_w, img_h, tokens, key_xy, B, *feats, *plist)
 
 
 def radar_head_apply(trainer, named_params, x0, ref, code, tokens, key_xy, B):
