@@ -386,6 +386,41 @@ TC_API int tc_add_rows(const float* a, const float* b, float* out, int32_t M, in
  * (query embedding, T:119-121). */
 TC_API int tc_period_sum(const float* x, float* out, int32_t batches, int32_t period, int32_t N, tc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N4  loss side (training variant).  Problems are indexed p = layer * B + sample over the `layers` output layers.
+ *   gt_boxes   [sumG, 9] fp32  (cx, cy, cz, w, l, h, rot, vx, vy), gravity centre (H:962-964), all samples concatenated
+ *   gt_labels  [sumG] int32;   gt_offsets [B + 1] int32: sample b owns rows gt_offsets[b] .. gt_offsets[b+1]-1
+ *
+ * tc_match_cost: cost [layers*B, Q, Gmax] fp32 = cls_weight * FocalLossCost(cls, label) + reg_weight * sum_j |bbox_j -
+ * normalize_bbox(gt)_j| (hungarian_assigner_3d.py:106-115, match_cost.py:15-26); columns >= G_b hold +inf. */
+typedef struct {
+  const float* cls; const float* bbox;            /* [layers*B, Q, classes], [layers*B, Q, 10] */
+  const float* gt_boxes; const int32_t* gt_labels; const int32_t* gt_offsets;
+  int32_t layers, B, Q, classes, Gmax;
+  float cls_weight, reg_weight, alpha, gamma, eps;
+  float* cost;
+} tc_match_cost_args;
+TC_API int tc_match_cost(const tc_match_cost_args* a, tc_stream_t stream);
+
+/* tc_detr_loss: sigmoid focal loss (mmdet FocalLoss, use_sigmoid, label weight 1) + code-weighted L1 loss on the matched
+ * rows (H:849-917) of every layer, with their gradients.
+ *   assigned  [layers*B, Q] int32: -1 = background, else the row of gt_boxes / gt_labels matched to the query
+ *   cls_avg / pos_avg [layers] fp32: the (already rank-averaged, >= 1) normalisers of H:885-897
+ *   loss_cls / loss_bbox [layers] fp32: ACCUMULATED (zero them first);  d_cls [layers*B, Q, classes], d_bbox [.., 10]: written
+ *   (may be NULL).  Rows whose normalised target is not finite carry no box loss (H:899). */
+typedef struct {
+  const float* cls; const float* bbox;
+  const int32_t* assigned;
+  const float* gt_boxes; const int32_t* gt_labels;
+  const float* code_weights;                      /* [10] */
+  const float* cls_avg; const float* pos_avg;
+  int32_t layers, B, Q, classes;
+  float alpha, gamma, loss_cls_weight, loss_bbox_weight;
+  float* loss_cls; float* loss_bbox;
+  float* d_cls; float* d_bbox;
+} tc_detr_loss_args;
+TC_API int tc_detr_loss(const tc_detr_loss_args* a, tc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,8 @@ def test_struct_layouts_match_header_field_order():
                        ("tc_radar_geometry_args", _lib.RadarGeometryArgs), ("tc_decode_args", _lib.DecodeArgs),
                        ("tc_layernorm_args", _lib.LayerNormArgs), ("tc_layernorm_bwd_args", _lib.LayerNormBwdArgs),
                        ("tc_attention_bwd_args", _lib.AttentionBwdArgs), ("tc_sample_bwd_args", _lib.SampleBwdArgs),
-                       ("tc_attention_dense_bwd_args", _lib.AttentionDenseBwdArgs)]:
+                       ("tc_attention_dense_bwd_args", _lib.AttentionDenseBwdArgs), ("tc_match_cost_args", _lib.MatchCostArgs),
+                       ("tc_detr_loss_args", _lib.DetrLossArgs)]:
         body = re.search(r"typedef struct \{([^}]*)\}\s*" + cname + ";", text).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []

@@ -128,6 +128,21 @@ class AttentionDenseBwdArgs(C.Structure):
                 ("workspace", _vp)]
 
 
+class MatchCostArgs(C.Structure):
+    _fields_ = [("cls", _vp), ("bbox", _vp), ("gt_boxes", _vp), ("gt_labels", _vp), ("gt_offsets", _vp),
+                ("layers", _i32), ("B", _i32), ("Q", _i32), ("classes", _i32), ("Gmax", _i32),
+                ("cls_weight", _f32), ("reg_weight", _f32), ("alpha", _f32), ("gamma", _f32), ("eps", _f32),
+                ("cost", _vp)]
+
+
+class DetrLossArgs(C.Structure):
+    _fields_ = [("cls", _vp), ("bbox", _vp), ("assigned", _vp), ("gt_boxes", _vp), ("gt_labels", _vp),
+                ("code_weights", _vp), ("cls_avg", _vp), ("pos_avg", _vp),
+                ("layers", _i32), ("B", _i32), ("Q", _i32), ("classes", _i32),
+                ("alpha", _f32), ("gamma", _f32), ("loss_cls_weight", _f32), ("loss_bbox_weight", _f32),
+                ("loss_cls", _vp), ("loss_bbox", _vp), ("d_cls", _vp), ("d_bbox", _vp)]
+
+
 # every symbol include/transcar_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "tc_abi_version": (C.c_int, []),
@@ -153,6 +168,8 @@ SYMBOLS = {
     "tc_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdArgs), _vp]),
     "tc_mask_grad": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),
     "tc_attention_sparse_bwd": (C.c_int, [C.POINTER(AttentionBwdArgs), _vp]),
+    "tc_match_cost": (C.c_int, [C.POINTER(MatchCostArgs), _vp]),
+    "tc_detr_loss": (C.c_int, [C.POINTER(DetrLossArgs), _vp]),
     "tc_sample_bwd": (C.c_int, [C.POINTER(SampleBwdArgs), _vp]),
     "tc_attention_dense_bwd": (C.c_int, [C.POINTER(AttentionDenseBwdArgs), _vp]),
     "tc_pointwise": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),

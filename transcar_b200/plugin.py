@@ -599,6 +599,27 @@ class Detr3DHead(nn.Module):
         cls_all, reg_all = radar_head_apply(self._trainer, named, x32.float(), ref, code, tokens, key_xy, B)
         return dict(all_cls_scores=cls_all, all_bbox_preds=reg_all, enc_cls_scores=None, enc_bbox_preds=None)
 
+    def loss(self, gt_bboxes_list, gt_labels_list, preds_dicts, gt_bboxes_ignore=None):
+        """Reference ``detr3d_head.py:919-1000``: Hungarian-matched focal + L1 losses of the three output layers ->
+        ``dict(loss_cls, loss_bbox, d0.loss_cls, d0.loss_bbox, d1.loss_cls, d1.loss_bbox)``.  Device cost matrices, host
+        scipy assignment, one fused loss + gradient kernel (``transcar_b200.loss``); the returned scalars are connected
+        to ``preds_dicts`` for ``backward()``."""
+        from .loss import Detr3DLoss, _LossFunction
+        assert gt_bboxes_ignore is None, f"{self.__class__.__name__} only supports for gt_bboxes_ignore setting to None."
+        if getattr(self, "_criterion", None) is None:
+            lc, lb = self.loss_cls_cfg or {}, self.loss_bbox_cfg or {}
+            self._criterion = Detr3DLoss(
+                num_classes=self.num_classes, pc_range=self.pc_range, code_weights=self.code_weights.tolist(),
+                loss_cls_weight=lc.get("loss_weight", 2.0), loss_bbox_weight=lb.get("loss_weight", 0.25),
+                alpha=lc.get("alpha", 0.25), gamma=lc.get("gamma", 2.0), sync_cls_avg_factor=self.sync_cls_avg_factor)
+        cls, bbox = preds_dicts["all_cls_scores"], preds_dicts["all_bbox_preds"]
+        losses = _LossFunction.apply(self._criterion, cls, bbox, gt_bboxes_list, gt_labels_list)
+        L = cls.shape[0]
+        out = {"loss_cls": losses[L - 1], "loss_bbox": losses[2 * L - 1]}
+        for l in range(L - 1):
+            out[f"d{l}.loss_cls"], out[f"d{l}.loss_bbox"] = losses[l], losses[L + l]
+        return out
+
     def get_bboxes(self, preds_dicts, img_metas, rescale=False):
         """Reference ``detr3d_head.py:1004-1023``: decode, move z from centre to box bottom, wrap in the
         sample's ``box_type_3d`` when the meta provides one."""
