@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--mode", default="infer", choices=["infer", "train", "full"],
                     help="infer = the fusion head (headline); train = radar-head training step + NCCL all-reduce; "
                          "full = images -> VoVNet-99 + FPN (cuDNN) -> fusion head (BASELINE.json configs[2])")
+    ap.add_argument("--unfrozen", action="store_true",
+                    help="--mode train: also train the DETR3D decoder (sampling backward + dense attention backward)")
     ap.add_argument("--full-batch", type=int, default=2, help="samples per GPU in --mode full (6 images of 928x1600 each)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
                     help="bf16x3 = tensor cores on split-bf16 operands (parity grade, default); bf16 = one pass")
@@ -588,33 +590,44 @@ def run_infer(args):
 
 # ------------------------------------------------------------------------------------------ GPU arm: training
 def run_train(args):
-    """BASELINE.json configs[4]: fusion-decoder training step with the NCCL gradient all-reduce.  Upstream gradients are
-    fixed random tensors (the Hungarian loss is host-side target assignment, out of scope N4)."""
+    """BASELINE.json configs[4]: fusion-decoder training step with the NCCL gradient all-reduce.  One step = head forward in
+    training mode (frozen decoder through the engine, or - ``--unfrozen`` - the decoder tape with the grid_sample scatter and
+    the dense attention backward) -> Hungarian-matched focal + L1 loss on synthetic ground truth (device cost matrices, host
+    scipy assignment, fused loss + gradient kernel) -> backward on library kernels -> ONE all-reduce of the gradient bucket."""
     import torch
     from transcar_b200 import _lib, sharding
-    from transcar_b200.training import trainable_names
+    from transcar_b200.training import decoder_trainable_names, trainable_names
     c = setup(args)
     world, dev, B = c.world, c.dev, args.batch
     head = c.head.train()
-    names = set(trainable_names(dict(head.named_parameters()).keys()))
-    for k, p in head.named_parameters():                      # reference recipe (tools/train.py:238-252)
+    keys = dict(head.named_parameters()).keys()
+    names = set(trainable_names(keys))                         # reference recipe (tools/train.py:238-252)
+    if args.unfrozen:
+        names |= set(decoder_trainable_names(keys))
+    for k, p in head.named_parameters():
         p.requires_grad_(k in names)
     params = [p for p in head.parameters() if p.requires_grad]
-    bucket = sharding.GradBucket(params, n_scalars=6)
+    bucket = sharding.GradBucket(params, n_scalars=0)
     dev_feats = [f.to(dev) for f in c.host_feats]
     g = torch.Generator().manual_seed(99 + c.rank)
-    Gc = torch.randn((3, B, 900, 10), generator=g).to(dev)
-    Gr = torch.randn((3, B, 900, 10), generator=g).to(dev)
+    gt_boxes, gt_labels = [], []
+    for _ in range(B):                                         # ~40 annotated objects per sample (nuScenes-like)
+        n = int(torch.randint(25, 55, (1,), generator=g))
+        b = torch.randn((n, 9), generator=g)
+        b[:, 0:2] *= 30.0
+        b[:, 3:6] = b[:, 3:6].abs() + 0.5
+        gt_boxes.append(b.to(dev))
+        gt_labels.append(torch.randint(0, 10, (n,), generator=g).to(dev))
 
     def step(reduce=True):
         bucket.zero()
         out = head(dev_feats, c.metas)
-        loss = (out["all_cls_scores"] * Gc).sum() + (out["all_bbox_preds"] * Gr).sum()
-        loss.backward()
+        losses = head.loss(gt_boxes, gt_labels, out)
+        total = sum(losses.values())
+        total.backward()
         if reduce:
-            bucket.scalars.fill_(1.0)                          # the six reduce_mean normalisers ride in the same call
             bucket.all_reduce()
-        return loss
+        return total
 
     n0 = _lib.launch_count()
     step()
@@ -632,12 +645,16 @@ def run_train(args):
     nparam = sum(p.numel() for p in params)
     line = {"metric": "fusion_decoder_train_samples_per_s", "value": world * B / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (radar-head forward/backward) + " + DTYPE_NAME[args.precision] + " (frozen decoder)",
-            "data": "synthetic", "config": workload_config(args),
-            "train": {"trainable_params": nparam, "allreduce_bytes": (nparam + 6) * 4,
+            "dtype": ("bf16x3 tcgen05 GEMMs (forward, dgrad, wgrad), fp32 everything else" if args.precision != "fp32"
+                      else "f32"),
+            "data": "synthetic", "config": dict(workload_config(args), unfrozen_decoder=bool(args.unfrozen)),
+            "train": {"trainable_params": nparam, "allreduce_bytes": nparam * 4,
                       "ms_per_step_without_allreduce": noar_ms, "exposed_allreduce_ms": ms - noar_ms,
-                      "what": "frozen DETR3D decoder forward (engine) + radar-head forward + backward on library kernels + "
-                              "one NCCL all-reduce of the flat gradient bucket + the six reduce_mean scalars"},
+                      "what": ("decoder tape (sampling backward = grid_sample scatter, dense attention backward)" if args.unfrozen
+                               else "frozen DETR3D decoder forward (engine)") +
+                              " + radar-head forward + Hungarian-matched focal/L1 loss (device costs, host scipy, fused loss+grad "
+                              "kernel, one 3-float all-reduce of the normalisers) + backward on library kernels + one NCCL "
+                              "all-reduce of the flat gradient bucket"},
             "gpu_launches": launches_per_step * steps, "gpu_launches_per_step": launches_per_step,
             "clocks": sampler.summary()}
     finish(c, line)

@@ -126,10 +126,22 @@ TC_API int tc_nchw_to_nhwc(const float* src, void* dst, int32_t dst_dtype, int32
  * path, one MMA pass (16-byte aligned rows, K >= 64) with SIMT fallback for the tiny odd shapes;  both TC_BF16X2 ->
  * tcgen05 "bf16x3" path: A is [M, 2K], W is [N, 2K] split bf16 (lda / ldw >= 2K, K % 64 == 0), three MMA passes
  * (hi*hi + lo*hi + hi*lo) into the same fp32 accumulator.
+ * tail (optional, N <= 32, no LayerNorm): a row-local stage fused behind the epilogue of the last Linear of a regression
+ * branch, so that the refinement / anchor / mask-geometry steps cost no launches of their own:
+ *   TC_TAIL_REF_UPDATE (T:195-203)  tail_ref_out[m, 0:3] = sigmoid(Y[m, {0,1,4}] + inverse_sigmoid(tail_in[m, 0:3]));
+ *                                   if tail_geom_out: the radar-mask geometry of H:543-567 from the NEW reference point
+ *                                   (x, y mapped to metres with tail_pc_range) and Y as the box code
+ *   TC_TAIL_BOX (H:596-600, :664-665, :722-723)  Y[m, 0:2] += anchor xy, Y[m, 4] += anchor z before Y is stored, anchor =
+ *                                   tail_in[m, {tail_xy_col, tail_xy_col + 1, tail_z_col}] (x, y mapped from [0,1] to metres
+ *                                   when tail_from_norm; z added as is: quirk Q3);  if tail_geom_out: the NEXT radar layer's
+ *                                   geometry (H:615-635 / H:671-693) from the updated Y
+ *   tail_geom_out rows are tc_radar_geometry's (cx, cy, fx, fy, rx, ry, radius, thr) with the clamp [tail_r_lo, tail_r_hi];
+ *   the arithmetic is the same device function the stand-alone kernels use (bit-identical masks).
  * out16_dtype selects the 16-bit output format: 0 or TC_BF16 -> bf16 [M, N];  TC_BF16X2 -> split bf16 [M, 2N]
  * (hi at column n, lo at column N + n; ld_out_bf16 >= 2N) - the A operand of the next bf16x3 Linear;  TC_F16 -> IEEE
  * half [M, N], saturated to +-65504 - the q/k/v operands of the dense attention core in bf16x3 mode.
  */
+enum { TC_TAIL_NONE = 0, TC_TAIL_REF_UPDATE = 1, TC_TAIL_BOX = 2 };
 typedef struct {
   const void* A;  int32_t a_dtype;  int64_t lda;      /* elements */
   const void* W;  int32_t w_dtype;  int64_t ldw;
@@ -145,6 +157,13 @@ typedef struct {
   float* out_f32;  int64_t ld_out_f32;
   void*  out_bf16; int64_t ld_out_bf16;
   int32_t out16_dtype;
+  int32_t tail;                                   /* TC_TAIL_NONE / TC_TAIL_REF_UPDATE / TC_TAIL_BOX */
+  const float* tail_in; int64_t ld_tail_in;
+  float* tail_ref_out;                            /* [M, 3] contiguous (TC_TAIL_REF_UPDATE) */
+  float* tail_geom_out;                           /* [M, 8] contiguous, optional */
+  int32_t tail_xy_col, tail_z_col, tail_from_norm;
+  float tail_pc_range[6];
+  float tail_r_lo, tail_r_hi;
 } tc_linear_args;
 TC_API int tc_linear(const tc_linear_args* a, tc_stream_t stream);
 

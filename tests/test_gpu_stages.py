@@ -496,3 +496,35 @@ def test_decode_ties_records_and_short_inputs(ops):
     top, idx = cls3.sigmoid().view(3, -1).topk(300, dim=1)
     torch.testing.assert_close(s3, top, rtol=0, atol=1e-7)
     assert torch.equal(l3.long(), idx % 10)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16x3"])
+def test_linear_fused_tails_match_the_standalone_kernels(ops, mode):
+    """tc_linear tails (reference update T:195-203; box anchor H:596-600 / :664-665 + next-layer mask geometry H:615-635)
+    produce bit-identical results to tc_ref_update / tc_box_anchor_add / tc_radar_geometry run after a plain tc_linear."""
+    M, K = 1800, 256
+    A, W, b = rnd((M, K), 1, 0.5), rnd((10, K), 2, K ** -0.5), rnd((10,), 3, 0.1)
+    if mode == "bf16":
+        A, W = A.bfloat16(), W.bfloat16()
+    elif mode == "bf16x3":
+        A, W = ops.cast_split(A), ops.cast_split(W)
+    ref = torch.rand((M, 3), generator=torch.Generator().manual_seed(5)).to(dev())
+    pc = synthetic.PC_RANGE
+    plain, _ = ops.linear(A, W, b)
+    # ---- reference update (+ geometry of the first radar layer)
+    tail = dict(kind="ref_update", ref=ref, pc_range=pc, geom=(1.0, 2.0))
+    y, _ = ops.linear(A, W, b, tail=tail)
+    assert torch.equal(y, plain)
+    want_ref = ops.ref_update(plain, ref)
+    assert torch.equal(tail["ref_out"], want_ref)
+    assert torch.equal(tail["geom_out"], ops.radar_geometry(want_ref, plain, pc, 1.0, 2.0, centre_is_normalised=True))
+    # ---- box anchor from normalised reference points (layer 1) and from a previous code (layers 2, 3)
+    for anchor, xy, z, norm, clamp in ((ref, 0, 2, True, (1.0, 2.0)), (rnd((M, 10), 7, 20.0), 0, 4, False, (0.5, 1.0))):
+        tail = dict(kind="box", anchor=anchor, xy_col=xy, z_col=z, from_norm=norm, pc_range=pc, geom=clamp)
+        out = torch.empty((3, M, 10), device=dev())[1]              # a strided destination like reg_all[li]
+        ops.linear(A, W, b, out_f32=out, tail=tail)
+        want = ops.box_anchor_add(plain.clone(), anchor, xy, z, norm, pc)
+        assert torch.equal(out, want)
+        assert torch.equal(tail["geom_out"], ops.radar_geometry(want, want, pc, *clamp, centre_is_normalised=False))
+    with pytest.raises(RuntimeError, match="tail needs"):
+        ops.linear(A, W, b, relu=True, tail=dict(kind="ref_update", ref=ref, pc_range=pc))

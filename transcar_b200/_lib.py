@@ -16,6 +16,7 @@ TC_F32, TC_BF16, TC_BF16X2, TC_F16 = 0, 1, 2, 3
 TC_MAX_LEVELS, TC_MAX_CAMS = 4, 8
 ABI_VERSION = 5
 TC_SAMPLE_ALL_CAMS = 1
+TC_TAIL_NONE, TC_TAIL_REF_UPDATE, TC_TAIL_BOX = 0, 1, 2
 TC_ATTN_AUTO, TC_ATTN_TENSOR, TC_ATTN_SIMT, TC_ATTN_SPARSE = 0, 1, 2, 3
 
 _vp, _i32, _i64, _f32, _u8p = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -44,7 +45,10 @@ class LinearArgs(C.Structure):
                 ("post_add", _vp), ("ld_post_add", _i64),
                 ("out_f32", _vp), ("ld_out_f32", _i64),
                 ("out_bf16", _vp), ("ld_out_bf16", _i64),
-                ("out16_dtype", _i32)]
+                ("out16_dtype", _i32),
+                ("tail", _i32), ("tail_in", _vp), ("ld_tail_in", _i64), ("tail_ref_out", _vp), ("tail_geom_out", _vp),
+                ("tail_xy_col", _i32), ("tail_z_col", _i32), ("tail_from_norm", _i32),
+                ("tail_pc_range", _f32 * 6), ("tail_r_lo", _f32), ("tail_r_hi", _f32)]
 
 
 class PointEmbedArgs(C.Structure):

@@ -194,22 +194,11 @@ __global__ void radar_geometry_kernel(const tc_radar_geometry_args a) {
     cy = __fadd_rn(__fmul_rn(cy, a.pc_range[4] - a.pc_range[1]), a.pc_range[1]);
   }
   const float* code = a.code + (long long)m * a.ld_code;
-  const float len = expf(code[3]);          // H:553
-  const float s = -code[6], c = -code[7];   // H:554-555
-  const float ox = __fmul_rn(__fmul_rn(len, 0.25f), s);     // object_length*0.25*object_rot_sin (left-assoc.)
-  const float oy = __fmul_rn(__fmul_rn(len, 0.25f), c);
-  float* g = a.geom + (long long)m * 8;
-  g[0] = cx; g[1] = cy;
-  g[2] = __fadd_rn(cx, ox); g[3] = __fadd_rn(cy, oy);
-  g[4] = __fsub_rn(cx, ox); g[5] = __fsub_rn(cy, oy);
-  const float radius = fminf(fmaxf(__fdiv_rn(len, 2.0f), a.r_lo), a.r_hi);
-  g[6] = radius;
-  // thr = smallest fp32 y with sqrt_rn(y) >= radius, so that  sqrt(x) < radius  <=>  x < thr  exactly (x >= 0).
-  // Lets the tensor-core attention kernel test squared distances without a square root per (query, key).
-  float thr = __fmul_rn(radius, radius);
-  for (int it = 0; it < 8 && thr > 0.f && __fsqrt_rn(thr) >= radius; ++it) thr = nextafterf(thr, 0.f);
-  for (int it = 0; it < 16 && __fsqrt_rn(thr) < radius; ++it) thr = nextafterf(thr, INFINITY);
-  g[7] = thr;
+  float g[8];
+  radar_geom_row(cx, cy, code[3], code[6], code[7], a.r_lo, a.r_hi, g);
+  float* o = a.geom + (long long)m * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = g[i];
 }
 
 __global__ void __launch_bounds__(256) radar_mask_kernel(const float* __restrict__ geom, const float* __restrict__ key_xy,

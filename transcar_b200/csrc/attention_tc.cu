@@ -463,15 +463,20 @@ int attention_tc_launch(const tc_attention_args* a, cudaStream_t s) {
   p.row_any = a->row_any;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    const int kMaxSmem = 110 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) { set_error("tc_attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
   static_assert(kSmemUsed + 1024 <= kSmemBytes, "shared-memory carve-up exceeds the request");
   dim3 grid((a->Lq + kBQ - 1) / kBQ, a->heads, a->B);
+  // Experiment hook: TC_ATTN_CTAS=3 pads the shared-memory request so that three (not four) CTAs share an SM, leaving
+  // 128 TMEM columns for the side-branch GEMMs that otherwise cannot become resident while attention runs.
+  static const int attn_ctas = [] { const char* e = getenv("TC_ATTN_CTAS"); return e ? atoi(e) : 4; }();
+  const size_t kSmemBytes = attn_ctas == 3 ? 73 * 1024 : (attn_ctas == 2 ? 110 * 1024 : (size_t)tc::kSmemBytes);
   cudaError_t le;
   if (f16) le = a->geom ? launch(attention_tc_kernel<true, true>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p)
                         : launch(attention_tc_kernel<false, true>, grid, dim3(kThreads), kSmemBytes, s, 1u, mq, mk, mv, p);

@@ -86,6 +86,18 @@ extern "C" int tc_linear(const tc_linear_args* a, tc_stream_t stream) {
   TC_REQUIRE(!a->out_f32 || a->ld_out_f32 >= a->N, TC_ERR_SHAPE, "tc_linear: ld_out_f32 < N");
   TC_REQUIRE(!a->out_bf16 || a->ld_out_bf16 >= (a->out16_dtype == TC_BF16X2 ? 2 : 1) * (int64_t)a->N, TC_ERR_SHAPE,
              "tc_linear: ld_out_bf16 < N (2N for a split output)");
+  if (a->tail != TC_TAIL_NONE) {
+    TC_REQUIRE(a->tail == TC_TAIL_REF_UPDATE || a->tail == TC_TAIL_BOX, TC_ERR_SHAPE, "tc_linear: unknown tail %d", a->tail);
+    TC_REQUIRE(a->N >= 8 && a->N <= 32 && !a->ln_gamma && !a->relu, TC_ERR_SHAPE,
+               "tc_linear: a tail needs 8 <= N <= 32, no LayerNorm and no ReLU (got N = %d)", a->N);
+    TC_REQUIRE(a->tail_in, TC_ERR_NULL, "tc_linear: tail_in is NULL");
+    TC_REQUIRE(a->tail != TC_TAIL_REF_UPDATE || (a->tail_ref_out && a->ld_tail_in >= 3), TC_ERR_NULL,
+               "tc_linear: TC_TAIL_REF_UPDATE needs tail_ref_out and ld_tail_in >= 3");
+    TC_REQUIRE(a->tail != TC_TAIL_BOX || (a->tail_xy_col >= 0 && a->tail_z_col >= 0 && a->ld_tail_in > a->tail_xy_col + 1 &&
+                                          a->ld_tail_in > a->tail_z_col), TC_ERR_SHAPE, "tc_linear: bad tail columns");
+    TC_REQUIRE(!a->tail_geom_out || aligned16(a->tail_geom_out), TC_ERR_ALIGN, "tc_linear: tail_geom_out must be 16-byte aligned");
+    TC_REQUIRE(a->out_f32 != nullptr, TC_ERR_NULL, "tc_linear: a tail needs the fp32 output");
+  }
   if (a->M == 0) return TC_OK;
   cudaStream_t s = as_stream(stream);
   if (linear_tc_supported(a)) return linear_tc_launch(a, s);

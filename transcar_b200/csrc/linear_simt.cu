@@ -30,6 +30,7 @@ struct LinearParams {
   float* out_f32; long long ld_out_f32;
   __nv_bfloat16* out_bf16; long long ld_out_bf16;
   int out16;             // TC_BF16, TC_BF16X2 (hi at column n, lo at column N + n) or TC_F16
+  TailParams tail;
   int vec_a, vec_w;      // 1: rows are 16-byte (fp32) / 8-byte (bf16) aligned and K % 4 == 0
 };
 
@@ -172,11 +173,26 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const LinearParams p) 
         if (n < p.N) y[j] = (y[j] - mean) * rstd * p.ln_gamma[n] + p.ln_beta[n];
       }
     }
+    if (p.tail.kind != TC_TAIL_NONE && n0 == 0) {
+      // columns 0..7 of the row live in lanes 0 .. 8/CPL-1: gather them, run the tail in lane 0, scatter the updates back
+      float r8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float mine = p.relu ? fmaxf(y[c % CPL], 0.f) : y[c % CPL];
+        r8[c] = __shfl_sync(0xffffffffu, mine, c / CPL);
+      }
+      if (lane == 0) apply_tail(p.tail, m, r8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float upd = __shfl_sync(0xffffffffu, r8[c], 0);
+        if (lane == c / CPL) y[c % CPL] = upd;          // relu (if any) already applied; values >= 0 stay put below
+      }
+    }
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const int n = nbase + j;
       if (n >= p.N) continue;
-      float v = p.relu ? fmaxf(y[j], 0.f) : y[j];
+      float v = (p.relu && p.tail.kind == TC_TAIL_NONE) ? fmaxf(y[j], 0.f) : y[j];
       if (p.post_add) v += p.post_add[(long long)m * p.ld_post_add + n];
       if (p.out_f32) p.out_f32[(long long)m * p.ld_out_f32 + n] = v;
       if (p.out_bf16) {
@@ -332,6 +348,7 @@ int linear_simt_launch(const tc_linear_args* a, cudaStream_t s) {
   p.out_f32 = a->out_f32; p.ld_out_f32 = a->ld_out_f32;
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); p.ld_out_bf16 = a->ld_out_bf16;
   p.out16 = a->out16_dtype == 0 ? TC_BF16 : a->out16_dtype;
+  p.tail = make_tail(a);
   const int ea = a->a_dtype == TC_F32 ? 4 : 2, ew = a->w_dtype == TC_F32 ? 4 : 2;
   p.vec_a = (a->K % 4 == 0) && ((a->lda * ea) % (4 * ea) == 0) && ((reinterpret_cast<uintptr_t>(a->A) % (4 * ea)) == 0);
   p.vec_w = (a->K % 4 == 0) && ((a->ldw * ew) % (4 * ew) == 0) && ((reinterpret_cast<uintptr_t>(a->W) % (4 * ew)) == 0);

@@ -42,11 +42,12 @@ constexpr uint32_t kBBytes = BN * BK * 2;
 constexpr int kMaxCluster = 4;                        // LayerNorm rows span at most 4 CTAs (N <= 256)
 // shared-memory carve-up per operand mode.  after the ring: barriers (full, empty, acc, init) + tmem slot, column
 // vectors (bias, gamma, beta), LN partials
-// kDeep: the 4-stage ring of the split mode (192 KB: one CTA per SM) for grids of at most one CTA per SM, where nothing
-// is gained by leaving room for a second CTA and a 2-stage ring serialises the K loop (N <= 64: 57 CTAs at M = 7200).
-template <bool kSplit, bool kDeep = false>
+// (Measured and rejected: a 4-stage, 192 KB ring for split-mode grids of at most one CTA per SM - N <= 64, 57 CTAs at
+// M = 7200.  5.0 vs ~6 us back to back, but inside the step such a CTA needs a whole SM to itself and waits behind the
+// co-running branch's kernels: +30 us per step.)
+template <bool kSplit>
 struct Cfg {
-  static constexpr int kStages = (kSplit && !kDeep) ? 2 : 4;
+  static constexpr int kStages = kSplit ? 2 : 4;
   static constexpr uint32_t kStageBytes = (kSplit ? 2u : 1u) * (kABytes + kBBytes);   // split: A_hi, A_lo, W_hi, W_lo
   static constexpr uint32_t kOffBars = kStages * kStageBytes;
   static constexpr uint32_t kOffVec = kOffBars + 128;
@@ -68,6 +69,7 @@ struct EpiParams {
   float* out_f32; long long ld_out_f32;
   __nv_bfloat16* out_bf16; long long ld_out_bf16;
   int out16;      // TC_BF16, TC_BF16X2 (hi at column n, lo at column N + n) or TC_F16
+  TailParams tail;
   int vec;        // 1: every row-wise operand is 32-byte aligned with a 32-byte multiple pitch -> 256-bit accesses
   int has_init;   // row_bias / residual(s) present
 };
@@ -142,10 +144,10 @@ __device__ __forceinline__ unsigned long long ld_smem_u64(uint32_t addr) {
   return v;
 }
 
-template <bool kLN, bool kSplit, bool kDeep>
-__global__ void __launch_bounds__(kThreads, kDeep ? 1 : 2)
+template <bool kLN, bool kSplit, bool kTail>
+__global__ void __launch_bounds__(kThreads, 2)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const EpiParams p) {
-  using C = Cfg<kSplit, kDeep>;
+  using C = Cfg<kSplit>;
   constexpr int kStages = C::kStages;
   constexpr uint32_t kStageBytes = C::kStageBytes, kOffBars = C::kOffBars, kOffVec = C::kOffVec, kOffPart = C::kOffPart;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -383,6 +385,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        if (kTail && c == 0 && row_ok && n0 == 0) apply_tail(p.tail, m, v);
         store_chunk(c, v);
       }
     } else {
@@ -501,22 +504,22 @@ bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CU
   return true;
 }
 
-template <bool kLN, bool kSplit, bool kDeep = false>
+template <bool kLN, bool kSplit, bool kTail = false>
 int launch_tile(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
   CUtensorMap ma, mw;
   const int kcols = kSplit ? 2 * a->K : a->K;       // split operands: [rows, 2K] = hi | lo
-  constexpr size_t kSmemBytes = Cfg<kSplit, kDeep>::kSmemBytes;
+  constexpr size_t kSmemBytes = Cfg<kSplit>::kSmemBytes;
   if (!get_map(a->A, a->lda, a->M, kcols, BM, &ma)) return TC_ERR_SHAPE;
   if (!get_map(a->W, a->ldw, a->N, kcols, BN, &mw)) return TC_ERR_SHAPE;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<kLN, kSplit, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<kLN, kSplit, kTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { set_error("tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
   const unsigned ntiles = (unsigned)((a->N + BN - 1) / BN);
   // LayerNorm: the CTAs of one row block form a cluster and exchange row statistics
-  cudaError_t e = launch(linear_tc_kernel<kLN, kSplit, kDeep>, dim3(ntiles, (unsigned)((a->M + BM - 1) / BM)), dim3(kThreads), kSmemBytes, s,
+  cudaError_t e = launch(linear_tc_kernel<kLN, kSplit, kTail>, dim3(ntiles, (unsigned)((a->M + BM - 1) / BM)), dim3(kThreads), kSmemBytes, s,
                          kLN ? ntiles : 1u, ma, mw, ep);
   if (e != cudaSuccess) { set_error("tc_linear(tcgen05): %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   count_launch();
@@ -569,20 +572,14 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   ep.out_f32 = a->out_f32; ep.ld_out_f32 = a->ld_out_f32;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16); ep.ld_out_bf16 = a->ld_out_bf16;
   ep.out16 = a->out16_dtype == 0 ? TC_BF16 : a->out16_dtype;
+  ep.tail = make_tail(a);
   ep.vec = epilogue_vectorizable(a) ? 1 : 0;
   ep.has_init = (a->row_bias || a->residual || a->residual2) ? 1 : 0;
   if (a->a_dtype == TC_BF16X2) {
-    static int sm_count = 0;
-    if (sm_count == 0) {
-      int dev = 0, n = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-      sm_count = n;
-    }
-    const long long ctas = (long long)((a->N + BN - 1) / BN) * ((a->M + BM - 1) / BM);
-    if (ctas <= sm_count && a->K > 2 * BK)        // at most one CTA per SM anyway: take the deep ring
-      return a->ln_gamma ? launch_tile<true, true, true>(a, ep, s) : launch_tile<false, true, true>(a, ep, s);
+    if (a->tail) return launch_tile<false, true, true>(a, ep, s);
     return a->ln_gamma ? launch_tile<true, true>(a, ep, s) : launch_tile<false, true>(a, ep, s);
   }
+  if (a->tail) return launch_tile<false, false, true>(a, ep, s);
   return a->ln_gamma ? launch_tile<true, false>(a, ep, s) : launch_tile<false, false>(a, ep, s);
 }
 

@@ -102,7 +102,7 @@ __device__ __forceinline__ void fetch_query(const SampleParams& p, int task, int
 
 // kOut: 0 = fp32 [.., C], 1 = bf16 [.., C], 2 = split bf16 [.., 2C] (hi | lo: the A operand of a bf16x3 Linear)
 template <bool kBf16In, int kOut, int kWarps, int kSlots>
-__global__ void __launch_bounds__(kWarps * 32, 1) sample_kernel(const SampleParams p) {
+__global__ void __launch_bounds__(kWarps * 32, kWarps <= 6 ? 2 : 1) sample_kernel(const SampleParams p) {
   constexpr bool kBf16Out = kOut != 0;
   constexpr int kOutRow = kOut == 2 ? 2 : 1;           // output row pitch in units of C
   constexpr int kPer = kBf16In ? 8 : 4;                 // channels per lane per chunk (16 bytes)
@@ -357,7 +357,8 @@ cudaError_t launch_sample(const SampleParams& p, long long total, int sm_count, 
     configured = true;
   }
   const long long ctas = (total + kWarps - 1) / kWarps;
-  return launch(kernel, dim3((unsigned)(ctas < sm_count ? ctas : sm_count)), dim3(kWarps * 32), (size_t)smem, s, 1u, p);
+  const long long resident = (long long)sm_count * (kWarps <= 6 ? 2 : 1);       // 6-warp CTAs (96 KB): two per SM
+  return launch(kernel, dim3((unsigned)(ctas < resident ? ctas : resident)), dim3(kWarps * 32), (size_t)smem, s, 1u, p);
 }
 
 // Tuning hook (tools/k1_bench.py): TC_SAMPLE_VARIANT picks the warps x ring-slots shape of the bf16 kernel.
@@ -420,8 +421,13 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   // 18.4 us, step +9 us: 768-thread CTAs start later), so 12 x 2 stays the default.
   if (bi && bo) {
     if (sample_variant() == 1) e = launch_sample<true, 1, 24, 1>(p, total, sm_count, s);
+    else if (sample_variant() == 2) e = launch_sample<true, 1, 6, 2>(p, total, sm_count, s);
     else e = launch_sample<true, 1, 12, 2>(p, total, sm_count, s);
-  } else if (bi && so) e = launch_sample<true, 2, 12, 2>(p, total, sm_count, s);
+    if (false) e = launch_sample<true, 1, 6, 2>(p, total, sm_count, s);
+  } else if (bi && so) {
+    if (sample_variant() == 2) e = launch_sample<true, 2, 6, 2>(p, total, sm_count, s);
+    else e = launch_sample<true, 2, 12, 2>(p, total, sm_count, s);
+  }
   else if (bi) e = launch_sample<true, 0, 12, 2>(p, total, sm_count, s);
   else if (so) e = launch_sample<false, 2, 12, 2>(p, total, sm_count, s);
   else if (bo) e = launch_sample<false, 1, 12, 2>(p, total, sm_count, s);

@@ -127,4 +127,78 @@ __device__ __forceinline__ bool radar_allowed(const Circle& c, const Circle& f, 
          (cdist_mm(r, kx, ky, knrm) < radius);
 }
 
+// ---- per-query circle geometry of the radar mask (H:543-567 / H:615-635 / H:671-693) -----------------------------
+// centre (cx, cy) in metres, box code columns 3 (log length), 6, 7 (heading terms) -> g[0..8) =
+// (cx, cy, fx, fy, rx, ry, radius, thr); thr = smallest fp32 y with sqrt_rn(y) >= radius, so that
+// sqrt(x) < radius  <=>  x < thr exactly (x >= 0).  ONE definition for tc_radar_geometry and the fused Linear tails.
+__device__ __forceinline__ void radar_geom_row(float cx, float cy, float code3, float code6, float code7, float r_lo, float r_hi,
+                                               float* g) {
+  const float len = expf(code3);            // H:553
+  const float s = -code6, c = -code7;       // H:554-555
+  const float ox = __fmul_rn(__fmul_rn(len, 0.25f), s);     // object_length*0.25*object_rot_sin (left-assoc.)
+  const float oy = __fmul_rn(__fmul_rn(len, 0.25f), c);
+  g[0] = cx; g[1] = cy;
+  g[2] = __fadd_rn(cx, ox); g[3] = __fadd_rn(cy, oy);
+  g[4] = __fsub_rn(cx, ox); g[5] = __fsub_rn(cy, oy);
+  const float radius = fminf(fmaxf(__fdiv_rn(len, 2.0f), r_lo), r_hi);
+  g[6] = radius;
+  float thr = __fmul_rn(radius, radius);
+  for (int it = 0; it < 8 && thr > 0.f && __fsqrt_rn(thr) >= radius; ++it) thr = nextafterf(thr, 0.f);
+  for (int it = 0; it < 16 && __fsqrt_rn(thr) < radius; ++it) thr = nextafterf(thr, INFINITY);
+  g[7] = thr;
+}
+
+// Row-local tails of tc_linear (include/transcar_b200.h): y = the row's first 8 outputs (columns 0..7), updated in place
+// for TC_TAIL_BOX.  Same operations, in the same order, as ref_update_kernel / box_anchor_add_kernel / radar_geometry_kernel.
+struct TailParams {
+  int kind;
+  const float* in; long long ld_in;
+  float* ref_out; float* geom_out;
+  int xy_col, z_col, from_norm;
+  float pc[6]; float r_lo, r_hi;
+};
+__device__ __forceinline__ void apply_tail(const TailParams& t, long long m, float* y) {
+  const float* in = t.in + m * t.ld_in;
+  if (t.kind == TC_TAIL_REF_UPDATE) {
+    const float r0 = sigmoid_f32(__fadd_rn(y[0], logit_f32(in[0])));
+    const float r1 = sigmoid_f32(__fadd_rn(y[1], logit_f32(in[1])));
+    const float r2 = sigmoid_f32(__fadd_rn(y[4], logit_f32(in[2])));
+    t.ref_out[m * 3 + 0] = r0; t.ref_out[m * 3 + 1] = r1; t.ref_out[m * 3 + 2] = r2;
+    if (t.geom_out) {
+      const float cx = __fadd_rn(__fmul_rn(r0, t.pc[3] - t.pc[0]), t.pc[0]);
+      const float cy = __fadd_rn(__fmul_rn(r1, t.pc[4] - t.pc[1]), t.pc[1]);
+      float g[8];
+      radar_geom_row(cx, cy, y[3], y[6], y[7], t.r_lo, t.r_hi, g);
+      float4* o = reinterpret_cast<float4*>(t.geom_out + m * 8);
+      o[0] = make_float4(g[0], g[1], g[2], g[3]);
+      o[1] = make_float4(g[4], g[5], g[6], g[7]);
+    }
+  } else if (t.kind == TC_TAIL_BOX) {
+    float ax = in[t.xy_col], ay = in[t.xy_col + 1];
+    const float az = in[t.z_col];
+    if (t.from_norm) {   // H:596-597; z is added un-scaled (quirk Q3, H:598 is an empty slice)
+      ax = __fadd_rn(__fmul_rn(ax, t.pc[3] - t.pc[0]), t.pc[0]);
+      ay = __fadd_rn(__fmul_rn(ay, t.pc[4] - t.pc[1]), t.pc[1]);
+    }
+    y[0] = __fadd_rn(y[0], ax);
+    y[1] = __fadd_rn(y[1], ay);
+    y[4] = __fadd_rn(y[4], az);
+    if (t.geom_out) {
+      float g[8];
+      radar_geom_row(y[0], y[1], y[3], y[6], y[7], t.r_lo, t.r_hi, g);
+      float4* o = reinterpret_cast<float4*>(t.geom_out + m * 8);
+      o[0] = make_float4(g[0], g[1], g[2], g[3]);
+      o[1] = make_float4(g[4], g[5], g[6], g[7]);
+    }
+  }
+}
+inline TailParams make_tail(const tc_linear_args* a) {
+  TailParams t;
+  t.kind = a->tail; t.in = a->tail_in; t.ld_in = a->ld_tail_in; t.ref_out = a->tail_ref_out; t.geom_out = a->tail_geom_out;
+  t.xy_col = a->tail_xy_col; t.z_col = a->tail_z_col; t.from_norm = a->tail_from_norm;
+  for (int i = 0; i < 6; ++i) t.pc[i] = a->tail_pc_range[i];
+  t.r_lo = a->tail_r_lo; t.r_hi = a->tail_r_hi;
+  return t;
+}
+
 }  // namespace tc

@@ -21,6 +21,8 @@ Precision modes (fp32 residual stream / LayerNorm / reference points / masks / a
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -28,6 +30,11 @@ from . import ops
 from .radar_tokens import MAX_RADAR_TOKENS, NUM_RADAR_FEATS, RADAR_PAD_VALUE
 
 RADIUS_CLAMP = ((1.0, 2.0), (1.0, 2.0), (0.5, 1.0))      # H:567, H:635, H:693
+# A/B switch.  Default: the sampling kernel waits for the WHOLE side branch (refined reference points + their position
+# feature).  TC_JOIN_SPLIT=1 lets it start right behind ref_update: measured 1.319 vs 1.324 ms per step (0.4 %), but the
+# sampling kernel then shares SMs with the branch's remaining GEMM (it needs whole SMs: 192 KB rings) and its in-step
+# duration grows from 18.4 to 25.2 us - not worth it.
+_JOIN_FULL = not os.environ.get("TC_JOIN_SPLIT")
 
 
 class FusionDecoderEngine:
@@ -151,6 +158,23 @@ class FusionDecoderEngine:
             torch.cuda.current_stream().wait_stream(self._side[k])
         self._keep.extend(t for t in tensors if t is not None)
 
+    def _mark_ref(self):
+        """Called on side stream 0 right after ref_update: lets the main stream wait for the reference points alone."""
+        self._ref_event = None
+        if self.use_branches and self._side is not None:
+            self._ref_event = torch.cuda.Event()
+            self._ref_event.record(torch.cuda.current_stream())
+
+    def _wait_ref(self, ref):
+        if _JOIN_FULL:
+            self._join(0, ref)
+            return
+        ev = getattr(self, "_ref_event", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._ref_event = None
+        self._keep.append(ref)
+
     # ------------------------------------------------------------------ helpers
     def _lin(self, x, key, **kw):
         """Linear by state-dict prefix with the engine's dtype policy: activations that only feed another GEMM
@@ -250,6 +274,8 @@ class FusionDecoderEngine:
         (the reference's ``Detr3DTransformerDecoder.forward`` signature, T:155-160) instead of the learned embedding;
         ``refine=False`` leaves the reference points untouched (``reg_branches is None``, T:190)."""
         Q, C, M = self.Q, self.C, B * self.Q
+        self._geom0 = None
+        self._ref_event = None           # never carry an event across forwards (a stale one would break graph capture)
         if init is None:
             x32, x16, ref = self._initial_state(B)
             rb_qkv, rb_aw, period = self.row_bias_qkv, self.row_bias_aw, Q
@@ -277,9 +303,9 @@ class FusionDecoderEngine:
             # --- Detr3DCrossAtten (T:302-378)
             aw = self._lin(x16, p + "attentions.1.attention_weights", bias=False,
                            row_bias=rb_aw[l], row_bias_period=period)
-            # join here, between the logits and the sampling launch: before the logits (+37 us per step) or after the
-            # sampling launch (+37 us) were both measured slower
-            self._join(0, pos_feat, ref)     # reference points refined by the previous layer + their position feature
+            # join the side branch (refined reference points + their position feature) between the logits and the sampling
+            # launch; see _JOIN_FULL for the measured alternative (wait for the reference points only)
+            self._wait_ref(ref)
             ev = self.sample_events
             if ev is not None:          # bench.py: per-launch CUDA-event timing of K1 on the launching stream
                 e0 = torch.cuda.Event(enable_timing=True, external=self.external_events)
@@ -294,6 +320,7 @@ class FusionDecoderEngine:
                 self.cam_masks.append(cam_mask)
             if l == max(self.L - 2, 0):
                 self._start_radar_branch()
+            self._join(0, pos_feat, ref)     # position feature of this layer's reference points (side branch)
             x32, x16 = self._lin(s.view(M, C), p + "attentions.1.output_proj", both=True,
                                  residual=x32, residual2=pos_feat, ln=self._ln(p + "norms.1"))
             # --- FFN (mmcv FFN: x + W2 relu(W1 x)) + norm
@@ -305,14 +332,22 @@ class FusionDecoderEngine:
                 if refine:
                     r = self._lin(x16, f"reg_branches.{l}.0", feed=True, relu=True)
                     r2 = self._lin(r, f"reg_branches.{l}.2", feed=True, relu=True)
-                    code = self._lin(r2, f"reg_branches.{l}.4")
-                    ref = ops.ref_update(code, ref)
+                    # last Linear of the refinement branch with the reference update (T:195-203) as its row-local tail; the
+                    # last layer's also emits the first radar layer's mask geometry (H:543-567)
+                    tail = dict(kind="ref_update", ref=ref, pc_range=self.pc_range,
+                                geom=RADIUS_CLAMP[0] if (self.has_radar and l == self.L - 1) else None)
+                    code = self._lin(r2, f"reg_branches.{l}.4", tail=tail)
+                    ref = tail["ref_out"]
+                    self._geom0 = tail.get("geom_out")
+                    self._keep.append(self._geom0)
+                    self._mark_ref()
                     self._keep.extend((x16, r, r2, code, ref))
                 if l + 1 < self.L:
                     pos_feat = self._position_encoder(f"transformer.decoder.layers.{l + 1}.", ref)
             if keep_all or l == self.L - 1:
                 hs.append(x32)
                 refs.append(ref)
+        self._ref_event = None           # the last refinement is joined as a whole branch (here or in radar_layers)
         if not defer_join:
             self._join(0, ref, code)
         return hs, refs, x32, x16, ref, code
@@ -409,8 +444,11 @@ class FusionDecoderEngine:
         for li in range(3):
             s = ("", "_2", "_3")[li]
             m = ("", "2", "3")[li]
-            lo, hi = RADIUS_CLAMP[li]
-            geom = ops.radar_geometry(anchor, code, self.pc_range, lo, hi, centre_is_normalised=centre_norm)
+            if li == 0:          # written by the tail of the decoder's last refinement Linear (else: stand-alone kernel)
+                geom = getattr(self, "_geom0", None)
+                if geom is None:
+                    geom = ops.radar_geometry(anchor, code, self.pc_range, *RADIUS_CLAMP[0], centre_is_normalised=True)
+                self._geom0 = None
             if li > 0:
                 self._join(1, qp)
             att, row_any = ops.attention(qp, KV[:, :, (2 * li) * C:(2 * li + 1) * C],
@@ -433,13 +471,15 @@ class FusionDecoderEngine:
             g = self._lin(x16, "final_reg" + m + ".0", feed=True, relu=True)
             g = self._lin(g, "final_reg" + m + ".2", feed=True, relu=True)
             reg = reg_all[li].view(M, n_code)
-            ops.linear(g, self.w["final_reg" + m + ".4.weight"], self.f32["final_reg" + m + ".4.bias"], out_f32=reg)
-            if li == 0:   # H:596-600: x,y of the refined reference in metres, z left normalised (quirk Q3)
-                ops.box_anchor_add(reg, anchor, 0, 2, True, self.pc_range)
-            else:         # H:664-665, H:722-723: previous stage's (cx, cy, cz) columns 0,1,4
-                ops.box_anchor_add(reg, anchor, 0, 4, False, self.pc_range)
+            # last Linear of the regression head; tail = anchor update (li == 0, H:596-600: x,y of the refined reference in
+            # metres, z left normalised - quirk Q3; else H:664-665 / H:722-723: previous stage's (cx, cy, cz) columns
+            # 0, 1, 4) + the NEXT radar layer's mask geometry (H:615-635 / H:671-693)
+            tail = dict(kind="box", anchor=anchor, xy_col=0, z_col=2 if li == 0 else 4, from_norm=li == 0,
+                        pc_range=self.pc_range, geom=RADIUS_CLAMP[li + 1] if li + 1 < 3 else None)
+            ops.linear(g, self.w["final_reg" + m + ".4.weight"], self.f32["final_reg" + m + ".4.bias"], out_f32=reg, tail=tail)
             aux[f"radar{li}.row_any"] = row_any
             aux[f"radar{li}.geom"] = geom
+            geom = tail.get("geom_out")
             anchor, code, centre_norm = reg, reg, False
             if li + 1 < 3:
                 qp = qp_next

@@ -171,10 +171,13 @@ def sample_fwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, out_d
 # --------------------------------------------------------------------------------------- K3
 def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, residual=None, residual2=None,
            ln=None, ln_eps=1e-5, relu=False, post_add=None, out_f32=None, out_bf16=None,
-           want_f32=True, want_bf16=False, out16="bf16"):
+           want_f32=True, want_bf16=False, out16="bf16", tail=None):
     """Y = epilogue(A @ W^T) - see ``tc_linear`` in include/transcar_b200.h.  A [M,K], W [N,K]; both fp32, both bf16
     or both :class:`SplitBf16` (bf16x3).  ``ln`` = (gamma, beta).  ``out16`` = format of the 16-bit output when
-    ``want_bf16``: 'bf16', 'split' (SplitBf16) or 'f16'.  Returns (out_f32 or None, 16-bit output or None)."""
+    ``want_bf16``: 'bf16', 'split' (SplitBf16) or 'f16'.  ``tail`` (N <= 32): a fused row-local stage,
+    ``dict(kind='ref_update', ref=[M,3], pc_range=, geom=(r_lo, r_hi) | None)`` or
+    ``dict(kind='box', anchor=[M,ld], xy_col=, z_col=, from_norm=, pc_range=, geom=(r_lo, r_hi) | None)``; its outputs are
+    returned in ``tail['ref_out']`` / ``tail['geom_out']``.  Returns (out_f32 or None, 16-bit output or None)."""
     lib = _lib.load()
     split = isinstance(A, SplitBf16)
     if split != isinstance(W, SplitBf16):
@@ -239,11 +242,27 @@ def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, 
         if o.shape != (M, 2 * N if a.out16_dtype == TC_BF16X2 else N):
             raise RuntimeError(f"transcar_b200.linear: 16-bit output has shape {tuple(o.shape)} for M, N = {(M, N)}")
         a.out_bf16, a.ld_out_bf16 = o.data_ptr(), ldo
+    if tail is not None:
+        tin, ldt = _rows(_need(tail["ref" if tail["kind"] == "ref_update" else "anchor"], "tail_in", torch.float32), "tail_in")
+        keep.append(tin)
+        a.tail = _lib.TC_TAIL_REF_UPDATE if tail["kind"] == "ref_update" else _lib.TC_TAIL_BOX
+        a.tail_in, a.ld_tail_in = tin.data_ptr(), ldt
+        for i in range(6):
+            a.tail_pc_range[i] = float(tail["pc_range"][i])
+        if tail["kind"] == "ref_update":
+            tail["ref_out"] = torch.empty((M, 3), device=A.device, dtype=torch.float32)
+            a.tail_ref_out = tail["ref_out"].data_ptr()
+        else:
+            a.tail_xy_col, a.tail_z_col, a.tail_from_norm = tail["xy_col"], tail["z_col"], 1 if tail["from_norm"] else 0
+        if tail.get("geom") is not None:
+            tail["geom_out"] = torch.empty((M, 8), device=A.device, dtype=torch.float32)
+            a.tail_geom_out = tail["geom_out"].data_ptr()
+            a.tail_r_lo, a.tail_r_hi = float(tail["geom"][0]), float(tail["geom"][1])
     label = "linear" if TIMELINE is None else (
         f"linear M{M} N{N} K{K} {'bf16x3' if split else 'bf16' if A.dtype == torch.bfloat16 else 'f32'}" + ("+rb" if row_bias is not None else "") +
         ("+gate" if row_gate is not None else "") + ("+res" if residual is not None else "") +
         ("+res2" if residual2 is not None else "") + ("+ln" if ln is not None else "") + ("+relu" if relu else "") +
-        ("+post" if post_add is not None else ""))
+        ("+post" if post_add is not None else "") + (f"+tail:{tail['kind']}" if tail is not None else ""))
     _lib.check(_call(label, lib.tc_linear, C.byref(a), _stream()), "linear")
     return out_f32, ret16
 
