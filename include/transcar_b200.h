@@ -218,6 +218,9 @@ typedef struct {
   void* out; int64_t ldo; int32_t out_dtype;
   uint8_t* row_any;
   int32_t algo;                /* tc_attention_algo; TC_ATTN_AUTO (0) picks the fastest exact path */
+  /* training variant: dropout on the attention probabilities (nn.MultiheadAttention(dropout=0.1), H:128 / mmcv attn_drop),
+   * mask = tc_dropout's for the logical [B*heads*Lq, Lk] tensor, row = (b * heads + h) * Lq + q.  SIMT and sparse paths. */
+  float dropout_p; uint64_t dropout_seed; uint64_t dropout_stream;
 } tc_attention_args;
 TC_API int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream);
 
@@ -340,6 +343,7 @@ typedef struct {
   const float* geom; const float* key_xy;
   float* dq; int64_t ld_dq;                      /* [B*Lq, heads*D] */
   float* dk; float* dv; int64_t ld_dk, ld_dv, dk_batch_stride, dv_batch_stride;
+  float dropout_p; uint64_t dropout_seed; uint64_t dropout_stream;     /* as in the forward call */
 } tc_attention_bwd_args;
 TC_API int tc_attention_sparse_bwd(const tc_attention_bwd_args* a, tc_stream_t stream);
 
@@ -387,6 +391,7 @@ typedef struct {
   float scale;
   float* dq; float* dk; float* dv;
   float* workspace;
+  float dropout_p; uint64_t dropout_seed; uint64_t dropout_stream;     /* as in the forward call */
 } tc_attention_dense_bwd_args;
 TC_API int tc_attention_dense_bwd(const tc_attention_dense_bwd_args* a, tc_stream_t stream);
 
@@ -397,6 +402,13 @@ TC_API int tc_attention_dense_bwd(const tc_attention_dense_bwd_args* a, tc_strea
  *   TC_PW_SIGMOID      out = sigmoid(x)                         (grad ignored, may be NULL) */
 enum { TC_PW_LOGIT_BWD = 0, TC_PW_SIGMOID_BWD = 1, TC_PW_LOGIT = 2, TC_PW_SIGMOID = 3 };
 TC_API int tc_pointwise(const float* grad, const float* x, float* out, int32_t n, int32_t mode, tc_stream_t stream);
+
+/* Dropout with a regenerable mask (training variant; rf_dropout* H:133-145, mmcv proj / ffn dropout):
+ *   out[m, n] = (residual ? residual[m, n] : 0) + keep(m, n) * x[m, n] / (1 - p),   keep ~ Bernoulli(1 - p)
+ * keep is a pure function of (seed, stream, m, n) (Philox4x32-10), so the backward pass applies the SAME call to the
+ * gradient instead of storing a mask.  x, residual, out: contiguous fp32 [M, N]; out may alias x or residual. */
+TC_API int tc_dropout(const float* x, const float* residual, float* out, int32_t M, int32_t N, float p, uint64_t seed,
+               uint64_t stream, tc_stream_t s);
 
 /* out[m, :] = a[m, :] + b[m % period, :]   ([M, N] fp32, contiguous; out may alias a).  The query_pos broadcast of the
  * decoder's training forward (q = k = x + query_pos) and gradient sums. */

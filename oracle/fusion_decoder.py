@@ -34,6 +34,16 @@ RADAR_PAD = 500.0
 RADIUS_CLAMP = ((1.0, 2.0), (1.0, 2.0), (0.5, 1.0))
 
 
+# Training-mode dropout of the reference (p = 0.1 at every site listed in transcar_b200/training.py).  The oracle does not
+# draw random numbers: a test installs ``DROPOUT = f(site, tensor, **ctx) -> tensor`` that multiplies by the SAME mask the
+# library regenerates from (seed, stream), so that gradients can be compared element by element.  None = eval mode.
+DROPOUT = None
+
+
+def _drop(site, t, **ctx):
+    return t if DROPOUT is None else DROPOUT(site, t, **ctx)
+
+
 # ------------------------------------------------------------------ small helpers
 def lin(sd, key, x):
     return F.linear(x, sd[key + ".weight"], sd[key + ".bias"])
@@ -49,10 +59,26 @@ def logit(x, eps=1e-5):
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
 
 
-def mha(sd, prefix, q, k, v, attn_mask=None):
+def mha(sd, prefix, q, k, v, attn_mask=None, site=None, **ctx):
     """``nn.MultiheadAttention(256, 8)`` slow path (``need_weights=True`` default: baddbmm ->
     softmax -> bmm, bool mask turned into -inf), eval mode.  q/k/v are ``[L,B,E]``.  H:578, and the
-    ``.attn`` member of mmcv's wrapper."""
+    ``.attn`` member of mmcv's wrapper.  With a ``DROPOUT`` hook installed the same steps are spelled out so that the
+    attention-probability dropout (``dropout=0.1`` of the module) can be applied with a given mask."""
+    if DROPOUT is not None:
+        E, H = q.shape[-1], NUM_HEADS
+        D = E // H
+        w, b = sd[prefix + ".in_proj_weight"], sd[prefix + ".in_proj_bias"]
+        Lq, B, _ = q.shape
+        Lk = k.shape[0]
+        qh = (F.linear(q, w[:E], b[:E]) * D ** -0.5).reshape(Lq, B * H, D).transpose(0, 1)
+        kh = F.linear(k, w[E:2 * E], b[E:2 * E]).reshape(Lk, B * H, D).transpose(0, 1)
+        vh = F.linear(v, w[2 * E:], b[2 * E:]).reshape(Lk, B * H, D).transpose(0, 1)
+        s = qh @ kh.transpose(1, 2)
+        if attn_mask is not None:
+            s = s.masked_fill(attn_mask.unsqueeze(0), float("-inf"))
+        pr = _drop(site + ".probs", s.softmax(-1), **ctx)                       # [B*H, Lq, Lk]
+        o = (pr @ vh).transpose(0, 1).reshape(Lq, B, E)
+        return F.linear(o, sd[prefix + ".out_proj.weight"], sd[prefix + ".out_proj.bias"])
     out, _ = F.multi_head_attention_forward(
         q, k, v, q.shape[-1], NUM_HEADS,
         sd[prefix + ".in_proj_weight"], sd[prefix + ".in_proj_bias"],
@@ -135,7 +161,7 @@ def cross_atten(sd, prefix, query, query_pos, mlvl_feats, ref, img_metas):
     p = logit(ref)
     p = F.relu(lnorm(sd, prefix + ".position_encoder.1", lin(sd, prefix + ".position_encoder.0", p)))
     p = F.relu(lnorm(sd, prefix + ".position_encoder.4", lin(sd, prefix + ".position_encoder.3", p)))
-    return out + residual + p.permute(1, 0, 2)
+    return _drop(prefix + ".cross_out", out) + residual + p.permute(1, 0, 2)      # T:378 self.dropout(output)
 
 
 # ------------------------------------------------------------------ a4: decoder layer (mmcv wrapper)
@@ -144,12 +170,12 @@ def decoder_layer(sd, prefix, query, query_pos, mlvl_feats, ref, img_metas):
     norm, ffn, norm)`` - cfg ``detr3d_res101_gridmask.py:65-82``; semantics per SURVEY appendix A."""
     x = query
     qk = x + query_pos
-    x = x + mha(sd, prefix + ".attentions.0.attn", qk, qk, x)
+    x = x + _drop(prefix + ".attn_out", mha(sd, prefix + ".attentions.0.attn", qk, qk, x, site=prefix))
     x = lnorm(sd, prefix + ".norms.0", x)
     x = cross_atten(sd, prefix + ".attentions.1", x, query_pos, mlvl_feats, ref, img_metas)
     x = lnorm(sd, prefix + ".norms.1", x)
-    h = F.relu(lin(sd, prefix + ".ffns.0.layers.0.0", x))
-    x = x + lin(sd, prefix + ".ffns.0.layers.1", h)
+    h = _drop(prefix + ".ffn_hidden", F.relu(lin(sd, prefix + ".ffns.0.layers.0.0", x)))
+    x = x + _drop(prefix + ".ffn_out", lin(sd, prefix + ".ffns.0.layers.1", h))
     x = lnorm(sd, prefix + ".norms.2", x)
     return x
 
@@ -236,7 +262,7 @@ def radar_block_mask(centre_xy, length, rot_s, rot_c, radar_xy, lo, hi):
 
 
 # ------------------------------------------------------------------ a12-a14: one radar layer
-def radar_layer(sd, idx, x, kv, blocked):
+def radar_layer(sd, idx, x, kv, blocked, sample=0):
     """H:573-593 for layer ``idx`` in {0,1,2}.  ``x [Q,1,C]``, ``kv [R,1,C]``, ``blocked [Q,R]``.
     Rows with no allowed key skip attention but still go through LN/FFN/LN (quirk Q6)."""
     s = ("", "_2", "_3")[idx]
@@ -244,11 +270,12 @@ def radar_layer(sd, idx, x, kv, blocked):
     rows = torch.where((blocked == False).any(dim=1))[0]      # noqa: E712
     x = x.clone()
     if rows.numel() > 0:
-        y = mha(sd, "rf_multihead_attn" + m, x[rows], kv, kv, attn_mask=blocked[rows])
-        x[rows] = x[rows] + y
+        y = mha(sd, "rf_multihead_attn" + m, x[rows], kv, kv, attn_mask=blocked[rows], site=f"radar{idx}", rows=rows,
+                sample=sample)
+        x[rows] = x[rows] + _drop(f"radar{idx}.attn_out", y, rows=rows, sample=sample)         # rf_dropout2 (H:581)
     x = lnorm(sd, "rf_norm2" + s, x)
-    h = F.relu(lin(sd, "rf_linear1" + s, x))
-    x = x + lin(sd, "rf_linear2" + s, h)
+    h = _drop(f"radar{idx}.ffn_hidden", F.relu(lin(sd, "rf_linear1" + s, x)), sample=sample)   # rf_dropout (H:584)
+    x = x + _drop(f"radar{idx}.ffn_out", lin(sd, "rf_linear2" + s, h), sample=sample)          # rf_dropout3 (H:585)
     x = lnorm(sd, "rf_norm3" + s, x)
     xt = x.permute(1, 0, 2)
     cls = cls_branch(sd, "final_cls" + m, xt)
@@ -288,7 +315,7 @@ def head_forward(sd, mlvl_feats, img_metas, num_layers=6, capture=None):
             rot_c = -tmp[..., 7]
             lo, hi = RADIUS_CLAMP[li]
             blocked = radar_block_mask(centre.clone(), length, rot_s, rot_c, radar_xy, lo, hi)
-            x, cls, reg, rows = radar_layer(sd, li, x, kv, blocked)
+            x, cls, reg, rows = radar_layer(sd, li, x, kv, blocked, sample=b)
             reg = reg.clone()
             reg[..., 0:2] = reg[..., 0:2] + ref_xy_m             # H:599, H:664, H:722
             reg[..., 4:5] = reg[..., 4:5] + ref_z                # H:600, H:665, H:723

@@ -79,6 +79,7 @@ def test_training_step_with_the_real_loss():
     head = plugin.build_head(cfg)
     head.load_state_dict(sd, strict=True)
     head = head.cuda().train()
+    head.train_dropout = 0.0
     names = set(trainable_names(sd.keys()))
     for k, p in head.named_parameters():
         p.requires_grad_(k in names)

@@ -23,6 +23,7 @@ def _setup(Q, B, seed, levels="tiny"):
     head = plugin.build_head(cfg)
     head.load_state_dict(sd, strict=True)
     head = head.cuda().train()
+    head.train_dropout = 0.0                                  # deterministic gradient checks; dropout has its own test
     feats = synthetic.make_feats(seed, B, levels)
     metas = synthetic.make_img_metas(B, seed=seed)
     return sd, head, feats, metas
@@ -150,6 +151,7 @@ def test_unfrozen_decoder_gradients_vs_oracle_autograd(precision):
     head = plugin.build_head(cfg)
     head.load_state_dict(sd, strict=True)
     head = head.cuda().train()
+    head.train_dropout = 0.0
     names = set(trainable_names(sd.keys())) | set(decoder_trainable_names(sd.keys()))
     for k, p in head.named_parameters():
         p.requires_grad_(k in names)
@@ -235,3 +237,81 @@ def test_trainer_gemm_backward_tensor_cores_vs_fp32():
     for a, b, what in zip(outs[0], outs[1], ("y", "dx", "dW", "db")):
         scale = float(a.abs().max())
         assert float((a - b).abs().max()) <= 3e-5 * scale, what
+
+
+def test_dropout_training_step_vs_oracle_with_identical_masks():
+    """Training-mode dropout (p = 0.1 at the reference's sites: attention probabilities, attention output, cross-attention
+    output, FFN hidden, FFN output - decoder and radar layers) with counter-based masks that the backward kernels
+    regenerate.  The oracle applies the SAME masks (materialised with tc_dropout on ones) through its DROPOUT hook, so
+    outputs and every gradient of the un-frozen recipe can be compared as in the dropout-free test."""
+    from transcar_b200 import ops, plugin
+    from transcar_b200.training import decoder_trainable_names, trainable_names
+    Q, B, seed, p_drop, rng_seed = 96, 2, 23, 0.1, 1234
+    sd = synthetic.make_state_dict(seed=seed, num_query=Q)
+    cfg = synthetic.head_config(num_query=Q)
+    cfg["precision"] = "fp32"
+    head = plugin.build_head(cfg)
+    head.load_state_dict(sd, strict=True)
+    head = head.cuda().train()
+    head.train_dropout, head.dropout_seed, head._train_step = p_drop, rng_seed, 3
+    names = set(trainable_names(sd.keys())) | set(decoder_trainable_names(sd.keys()))
+    for k, p in head.named_parameters():
+        p.requires_grad_(k in names)
+    feats = synthetic.make_feats(seed, B, "tiny", smooth=True)
+    metas = synthetic.make_img_metas(B, seed=seed)
+    feats_c = [ops.to_channels_last(f.cuda()) for f in feats]
+    g = torch.Generator().manual_seed(5)
+    Gc, Gr = torch.randn((3, B, Q, 10), generator=g).cuda(), torch.randn((3, B, Q, 10), generator=g).cuda()
+    out = head(feats_c, metas)
+    ((out["all_cls_scores"] * Gc).sum() + (out["all_bbox_preds"] * Gr).sum()).backward()
+    # a second forward draws different masks (the step counter advanced)
+    with torch.no_grad():
+        out2 = head(feats_c, metas)
+    assert not torch.equal(out2["all_cls_scores"], out["all_cls_scores"])
+
+    KIND = {"probs": 0, "attn_out": 1, "cross_out": 2, "ffn_hidden": 3, "ffn_out": 4}
+    H, R, C, step = 8, 1500, 256, 3
+
+    def mask(layer, kind, rows, cols):
+        return ops.dropout(torch.ones((rows, cols), device="cuda"), p_drop, rng_seed, step * 1024 + layer * 8 + KIND[kind])
+
+    def hook(site, t, rows=None, sample=0):
+        kind = site.rsplit(".", 1)[1]
+        if site.startswith("radar"):
+            layer = 6 + int(site[5])
+            if kind == "probs":                    # [H, Nsel, R] of one sample
+                return t * mask(layer, kind, B * H * Q, R).view(B, H, Q, R)[sample][:, rows, :]
+            m = mask(layer, kind, B * Q, t.shape[-1]).view(B, Q, -1)[sample]
+            return t * (m if rows is None else m[rows]).unsqueeze(1)
+        layer = int(site.split("layers.")[1].split(".")[0])
+        if kind == "probs":                        # [B*H, Q, Q]
+            return t * mask(layer, kind, B * H * Q, Q).view(B * H, Q, Q)
+        return t * mask(layer, kind, B * Q, t.shape[-1]).view(B, Q, -1).permute(1, 0, 2)     # oracle tensors are [Q, B, C]
+
+    sd_g = {k: v.cuda().clone().requires_grad_(k in names) for k, v in sd.items()}
+    O.DROPOUT = hook
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = O.head_forward(sd_g, [f.cuda() for f in feats], metas)
+    finally:
+        O.DROPOUT = None
+    ((want["all_cls_scores"] * Gc).sum() + (want["all_bbox_preds"] * Gr).sum()).backward()
+    torch.testing.assert_close(out["all_cls_scores"], want["all_cls_scores"], rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(out["all_bbox_preds"], want["all_bbox_preds"], rtol=1e-4, atol=2e-4)
+    got = dict(head.named_parameters())
+    worst = ("", 0.0)
+    for k in sorted(names):
+        gk, wk = got[k].grad, sd_g[k].grad
+        if ".attentions.0.attn.in_proj_bias" in k:
+            gk, wk = gk.clone(), wk.clone()
+            gk[256:512] = 0
+            wk[256:512] = 0
+        scale = max(float(wk.abs().max()), 1e-3)
+        err = float((gk - wk).abs().max())
+        worst = max(worst, (k, err / scale), key=lambda x: x[1])
+        assert err <= 2e-3 * scale + 2e-5, f"{k}: max |dgrad| {err:.3e} vs scale {scale:.3e}"
+    print(f"[dropout] worst relative gradient deviation {worst[1]:.2e} ({worst[0]})")
+    # the mask statistics are those of Bernoulli(1 - p) scaled by 1 / (1 - p)
+    m = mask(0, "ffn_out", 4096, 256)
+    assert abs(float((m > 0).float().mean()) - (1 - p_drop)) < 2e-3 and float(m.max()) == pytest.approx(1 / (1 - p_drop))

@@ -6,7 +6,6 @@ run() {
 import json,sys; d=json.load(open('gpurun_out/ab.json')); r=d['roofline']; print('$*', 'samples/s %.0f fwd %.4f k1 %.2f us frac %.3f iso %.2f' % (d['value'], d['step']['forward_ms'], r['avg_launch_ms']*1e3, r['frac'], r['isolated']['avg_launch_ms']*1e3))" || tail -3 gpurun_out/ab.err
 }
 run A=0
-run TC_NO_DEEP_RING=1
+run TC_CLS_LATE=1
 run A=0
-run TC_NO_DEEP_RING=1
-run TC_DISABLE_PDL=1
+run TC_CLS_LATE=1

@@ -66,7 +66,8 @@ class AttentionArgs(C.Structure):
                 ("scale", _f32),
                 ("geom", _vp), ("key_xy", _vp),
                 ("out", _vp), ("ldo", _i64), ("out_dtype", _i32),
-                ("row_any", _vp), ("algo", _i32)]
+                ("row_any", _vp), ("algo", _i32),
+                ("dropout_p", _f32), ("dropout_seed", C.c_uint64), ("dropout_stream", C.c_uint64)]
 
 
 class RadarGeometryArgs(C.Structure):
@@ -109,7 +110,8 @@ class AttentionBwdArgs(C.Structure):
                 ("scale", _f32),
                 ("geom", _vp), ("key_xy", _vp),
                 ("dq", _vp), ("ld_dq", _i64),
-                ("dk", _vp), ("dv", _vp), ("ld_dk", _i64), ("ld_dv", _i64), ("dk_batch_stride", _i64), ("dv_batch_stride", _i64)]
+                ("dk", _vp), ("dv", _vp), ("ld_dk", _i64), ("ld_dv", _i64), ("dk_batch_stride", _i64), ("dv_batch_stride", _i64),
+                ("dropout_p", _f32), ("dropout_seed", C.c_uint64), ("dropout_stream", C.c_uint64)]
 
 
 class SampleBwdArgs(C.Structure):
@@ -129,7 +131,8 @@ class AttentionDenseBwdArgs(C.Structure):
                 ("B", _i32), ("Lq", _i32), ("Lk", _i32), ("heads", _i32), ("D", _i32),
                 ("scale", _f32),
                 ("dq", _vp), ("dk", _vp), ("dv", _vp),
-                ("workspace", _vp)]
+                ("workspace", _vp),
+                ("dropout_p", _f32), ("dropout_seed", C.c_uint64), ("dropout_stream", C.c_uint64)]
 
 
 class MatchCostArgs(C.Structure):
@@ -177,6 +180,7 @@ SYMBOLS = {
     "tc_sample_bwd": (C.c_int, [C.POINTER(SampleBwdArgs), _vp]),
     "tc_attention_dense_bwd": (C.c_int, [C.POINTER(AttentionDenseBwdArgs), _vp]),
     "tc_pointwise": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "tc_dropout": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, C.c_uint64, C.c_uint64, _vp]),
     "tc_add_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "tc_period_sum": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
 }

@@ -21,6 +21,7 @@ struct AttnParams {
   const float* geom; const float* key_xy;
   void* out; long long ldo;
   uint8_t* row_any;
+  DropoutRng rng;          // p == 0: no dropout
 };
 
 template <bool kBf16>
@@ -148,8 +149,10 @@ __global__ void __launch_bounds__(kRows) attention_simt_kernel(const AttnParams 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (!ok[j]) continue;
-        const float pj = expf(s[j] - mnew);
+        float pj = expf(s[j] - mnew);
         lrun += pj;
+        if (p.rng.p > 0.f)           // attention-probability dropout: the normaliser keeps every key, the sum over V does not
+          pj *= dropout_scale(p.rng, (uint32_t)((b * p.heads + h) * p.Lq + row), (uint32_t)(k0 + j0 + j));
         const float4* vr = reinterpret_cast<const float4*>(&Vs[j0 + j][0]);
 #pragma unroll
         for (int d4 = 0; d4 < kD / 4; ++d4) {
@@ -232,6 +235,7 @@ int attention_simt_launch(const tc_attention_args* a, cudaStream_t s) {
   p.B = a->B; p.Lq = a->Lq; p.Lk = a->Lk; p.heads = a->heads;
   p.scale = a->scale; p.geom = a->geom; p.key_xy = a->key_xy;
   p.out = a->out; p.ldo = a->ldo; p.row_any = a->row_any;
+  p.rng = make_rng(a->dropout_p, a->dropout_seed, a->dropout_stream);
   dim3 grid((a->Lq + kRows - 1) / kRows, a->heads, a->B);
   const bool bi = a->qkv_dtype == TC_BF16, bo = a->out_dtype == TC_BF16, mk = a->geom != nullptr;
 #define TC_ATTN_LAUNCH(BI, BO, MK) attention_simt_kernel<BI, BO, MK><<<grid, kRows, 0, s>>>(p)

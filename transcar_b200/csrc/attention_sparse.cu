@@ -28,6 +28,7 @@ struct SparseParams {
   void* out; long long ldo;
   int out_split;          // 16-bit output is split bf16 [.., 2*256]: hi | lo
   uint8_t* row_any;
+  DropoutRng rng;         // p == 0: no dropout
 };
 
 template <bool kBf16>
@@ -130,8 +131,10 @@ __global__ void __launch_bounds__(kWarps * 32) attention_sparse_kernel(const Spa
         const float corr = expf(m_run - m_new);               // m_run = -inf -> 0
         const float pj = expf(s - m_new);
         l_run = fmaf(l_run, corr, pj);
+        // attention-probability dropout (training): the normaliser keeps every key, the sum over V does not
+        const float pd = p.rng.p > 0.f ? pj * dropout_scale(p.rng, (uint32_t)((b * 8 + (lane >> 2)) * p.Lq + q), (uint32_t)j) : pj;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], corr, pj * vv[i]);
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], corr, pd * vv[i]);
         m_run = m_new;
       }
       }
@@ -178,6 +181,7 @@ int attention_sparse_launch(const tc_attention_args* a, cudaStream_t s) {
   p.scale = a->scale; p.geom = a->geom; p.key_xy = a->key_xy;
   p.out = a->out; p.ldo = a->ldo; p.row_any = a->row_any;
   p.out_split = a->out_dtype == TC_BF16X2 ? 1 : 0;
+  p.rng = make_rng(a->dropout_p, a->dropout_seed, a->dropout_stream);
   dim3 grid((a->Lq + kWarps - 1) / kWarps, a->B);
   const bool bi = a->qkv_dtype == TC_BF16, bo = a->out_dtype == TC_BF16 || a->out_dtype == TC_BF16X2;
   if (bi && bo) launch(attention_sparse_kernel<true, true>, grid, dim3(kWarps * 32), 0, s, 1u, p);

@@ -203,6 +203,7 @@ struct SparseBwdParams {
   const float* geom; const float* key_xy;
   float* dq; long long ld_dq;
   float* dk; float* dv; long long ld_dk, ld_dv, dkbs, dvbs;
+  DropoutRng rng;
 };
 
 __device__ __forceinline__ void ld8(const float* p, float (&d)[8]) {
@@ -289,22 +290,25 @@ __global__ void __launch_bounds__(kWarps * 32) attention_sparse_bwd_kernel(const
           for (int i = 0; i < 8; ++i) s = fmaf(qv[i], kv[i], s);
           s += __shfl_xor_sync(0xffffffffu, s, 1);
           s += __shfl_xor_sync(0xffffffffu, s, 2);
+          // same dropout decision as the forward kernel: O = sum_j (drop_j p_j) v_j, normaliser un-dropped
+          const float drop = p.rng.p > 0.f ? dropout_scale(p.rng, (uint32_t)((b * 8 + (lane >> 2)) * p.Lq + q), (uint32_t)j) : 1.0f;
           if (pass == 0) {
             const float m_new = fmaxf(m_run, s);
             const float corr = expf(m_run - m_new);
             const float pj = expf(s - m_new);
             l_run = fmaf(l_run, corr, pj);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) oacc[i] = fmaf(oacc[i], corr, pj * vv[i]);
+            for (int i = 0; i < 8; ++i) oacc[i] = fmaf(oacc[i], corr, pj * drop * vv[i]);
             m_run = m_new;
           } else {
-            const float pj = expf(s - m_run) * inv_l;
+            const float pt = expf(s - m_run) * inv_l;       // softmax probability
+            const float pj = pt * drop;                      // what multiplied V in the forward
             float dP = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) dP = fmaf(dO[i], vv[i], dP);
             dP += __shfl_xor_sync(0xffffffffu, dP, 1);
             dP += __shfl_xor_sync(0xffffffffu, dP, 2);
-            const float dS = pj * (dP - D);
+            const float dS = pt * (dP * drop - D);
             float* dkr = p.dk + (long long)b * p.dkbs + (long long)j * p.ld_dk + lane * 8;
             float* dvr = p.dv + (long long)b * p.dvbs + (long long)j * p.ld_dv + lane * 8;
 #pragma unroll
@@ -344,6 +348,7 @@ struct DenseBwdParams {
   int B, Lq, Lk, heads;
   float scale;
   float* dq; float* dk; float* dv; float* lse; float* delta;
+  DropoutRng rng;
 };
 constexpr int kBwdRows = 128, kBwdTile = 32, kHD = 32;
 
@@ -387,6 +392,7 @@ __global__ void __launch_bounds__(kBwdRows) attn_dense_bwd_dq_kernel(const Dense
           float dp = 0.f;
 #pragma unroll
           for (int d = 0; d < kHD; ++d) dp = fmaf(go[d], sv[r][d], dp);
+          if (p.rng.p > 0.f) dp *= dropout_scale(p.rng, (uint32_t)((b * p.heads + h) * p.Lq + i), (uint32_t)(j0 + r));
           const float ds = pij * (dp - delta);
 #pragma unroll
           for (int d = 0; d < kHD; ++d) acc[d] = fmaf(ds, sk[r][d], acc[d]);
@@ -434,9 +440,12 @@ __global__ void __launch_bounds__(kBwdRows) attn_dense_bwd_dkv_kernel(const Dens
 #pragma unroll
       for (int d = 0; d < kHD; ++d) { sc = fmaf(sq[r][d], k[d], sc); dp = fmaf(sg[r][d], v[d], dp); }
       const float pij = expf(sc - s_lse[r]);
-      const float ds = pij * (dp - s_delta[r]);
+      const float drop = (p.rng.p > 0.f && ok && i0 + r < p.Lq)
+                             ? dropout_scale(p.rng, (uint32_t)((b * p.heads + h) * p.Lq + i0 + r), (uint32_t)j) : 1.0f;
+      const float ds = pij * (dp * drop - s_delta[r]);
+      const float pd = pij * drop;
 #pragma unroll
-      for (int d = 0; d < kHD; ++d) { dv[d] = fmaf(pij, sg[r][d], dv[d]); dk[d] = fmaf(ds, sq[r][d], dk[d]); }   // sq already holds scale * q
+      for (int d = 0; d < kHD; ++d) { dv[d] = fmaf(pd, sg[r][d], dv[d]); dk[d] = fmaf(ds, sq[r][d], dk[d]); }   // sq already holds scale * q
     }
   }
   if (!ok) return;
@@ -465,6 +474,21 @@ __global__ void pointwise_kernel(const float* __restrict__ grad, const float* __
     if (1.0f - xv >= eps) d += 1.0f / bq;
   }
   out[i] = g * d;
+}
+
+__global__ void dropout_kernel(const float* __restrict__ x, const float* __restrict__ residual, float* __restrict__ out, int M,
+                               int N4, const DropoutRng rng) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // one thread = 4 consecutive columns = one Philox block
+  if (i >= (long long)M * N4) return;
+  const int m = (int)(i / N4), c4 = (int)(i % N4);
+  const uint4 r = philox4((uint32_t)c4, (uint32_t)m, rng);
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  float4 o = residual ? reinterpret_cast<const float4*>(residual)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  o.x += keep_from(r.x, rng.p) ? v.x * rng.inv_keep : 0.f;
+  o.y += keep_from(r.y, rng.p) ? v.y * rng.inv_keep : 0.f;
+  o.z += keep_from(r.z, rng.p) ? v.z * rng.inv_keep : 0.f;
+  o.w += keep_from(r.w, rng.p) ? v.w * rng.inv_keep : 0.f;
+  reinterpret_cast<float4*>(out)[i] = o;
 }
 
 __global__ void add_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n4,
@@ -501,7 +525,8 @@ extern "C" int tc_attention_dense_bwd(const tc_attention_dense_bwd_args* a, tc_s
   DenseBwdParams p{a->q, a->k, a->v, a->o, a->dout, a->ldq, a->ldk, a->ldv, a->ldo, a->ld_dout,
                    a->q_batch_stride, a->k_batch_stride, a->v_batch_stride, a->o_batch_stride, a->dout_batch_stride,
                    a->B, a->Lq, a->Lk, a->heads, a->scale, a->dq, a->dk, a->dv,
-                   a->workspace, a->workspace + (long long)a->B * a->heads * a->Lq};
+                   a->workspace, a->workspace + (long long)a->B * a->heads * a->Lq,
+                   make_rng(a->dropout_p, a->dropout_seed, a->dropout_stream)};
   cudaStream_t s = as_stream(stream);
   attn_dense_bwd_dq_kernel<<<dim3((a->Lq + kBwdRows - 1) / kBwdRows, a->heads, a->B), kBwdRows, 0, s>>>(p);
   attn_dense_bwd_dkv_kernel<<<dim3((a->Lk + kBwdRows - 1) / kBwdRows, a->heads, a->B), kBwdRows, 0, s>>>(p);
@@ -518,6 +543,20 @@ extern "C" int tc_pointwise(const float* grad, const float* x, float* out, int32
   pointwise_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(grad, x, out, n, mode);
   count_launch();
   return check_launch("tc_pointwise");
+}
+
+extern "C" int tc_dropout(const float* x, const float* residual, float* out, int32_t M, int32_t N, float p, uint64_t seed,
+                          uint64_t stream, tc_stream_t s) {
+  using namespace tc;
+  TC_REQUIRE(x && out, TC_ERR_NULL, "tc_dropout: NULL pointer");
+  TC_REQUIRE(M >= 0 && N > 0 && N % 4 == 0, TC_ERR_SHAPE, "tc_dropout: N must be a positive multiple of 4 (got %d)", N);
+  TC_REQUIRE(p >= 0.f && p < 1.f, TC_ERR_SHAPE, "tc_dropout: p must be in [0, 1)");
+  TC_REQUIRE(aligned16(x) && aligned16(out) && (!residual || aligned16(residual)), TC_ERR_ALIGN, "tc_dropout: 16-byte alignment");
+  if (M == 0) return TC_OK;
+  const long long n4 = (long long)M * (N / 4);
+  dropout_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(s)>>>(x, residual, out, M, N / 4, make_rng(p, seed, stream));
+  count_launch();
+  return check_launch("tc_dropout");
 }
 
 extern "C" int tc_add_rows(const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t period, tc_stream_t stream) {
@@ -646,6 +685,7 @@ extern "C" int tc_attention_sparse_bwd(const tc_attention_bwd_args* a, tc_stream
   p.dq = a->dq; p.ld_dq = a->ld_dq;
   p.dk = a->dk; p.dv = a->dv; p.ld_dk = a->ld_dk; p.ld_dv = a->ld_dv;
   p.dkbs = a->dk_batch_stride; p.dvbs = a->dv_batch_stride;
+  p.rng = make_rng(a->dropout_p, a->dropout_seed, a->dropout_stream);
   dim3 grid((a->Lq + kWarps - 1) / kWarps, a->B);
   launch(attention_sparse_bwd_kernel, grid, dim3(kWarps * 32), 0, as_stream(stream), 1u, p);
   count_launch();

@@ -129,8 +129,15 @@ extern "C" int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream) 
   TC_REQUIRE(a->algo >= TC_ATTN_AUTO && a->algo <= TC_ATTN_SPARSE, TC_ERR_SHAPE, "tc_attention_fwd: unknown algo %d", a->algo);
   TC_REQUIRE(!a->key_xy || (reinterpret_cast<uintptr_t>(a->key_xy) & 7u) == 0, TC_ERR_ALIGN,
              "tc_attention_fwd: key_xy must be 8-byte aligned");
+  TC_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, TC_ERR_SHAPE, "tc_attention_fwd: dropout_p must be in [0, 1)");
   if (a->B == 0 || a->Lq == 0) return TC_OK;
   cudaStream_t s = as_stream(stream);
+  if (a->dropout_p > 0.f) {        // training variant: probability dropout lives in the fp32 kernels only
+    TC_REQUIRE(a->algo != TC_ATTN_TENSOR && a->qkv_dtype != TC_F16 && a->out_dtype != TC_BF16X2, TC_ERR_DTYPE,
+               "tc_attention_fwd: dropout is supported on the SIMT and sparse paths");
+    if (a->algo != TC_ATTN_SIMT && attention_sparse_supported(a)) return attention_sparse_launch(a, s);
+    return attention_simt_launch(a, s);
+  }
   switch (a->algo) {
     case TC_ATTN_SPARSE:
       TC_REQUIRE(attention_sparse_supported(a), TC_ERR_SHAPE, "tc_attention_fwd: sparse path needs geom/key_xy and 8 heads x 32");

@@ -127,6 +127,43 @@ __device__ __forceinline__ bool radar_allowed(const Circle& c, const Circle& f, 
          (cdist_mm(r, kx, ky, knrm) < radius);
 }
 
+// ---- counter-based dropout (training variant) ---------------------------------------------------------------------
+// Philox4x32-10 keyed by (seed, stream); element (row, col) of a logical 2-D tensor takes component col & 3 of the block with
+// counter (col >> 2, row).  A mask is a pure function of (seed, stream, row, col): the backward kernels regenerate it
+// instead of storing it, and tc_dropout on a tensor of ones materialises it for the parity tests.  Semantics of
+// nn.Dropout / the attention-probability dropout of nn.MultiheadAttention (H:122-145, H:578): keep with probability 1 - p,
+// scale kept values by 1 / (1 - p).
+struct DropoutRng {
+  float p, inv_keep;
+  uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
+};
+inline DropoutRng make_rng(float p, uint64_t seed, uint64_t stream) {
+  DropoutRng r;
+  r.p = p; r.inv_keep = p < 1.f ? 1.0f / (1.0f - p) : 0.f;
+  r.seed_lo = (uint32_t)seed; r.seed_hi = (uint32_t)(seed >> 32);
+  r.stream_lo = (uint32_t)stream; r.stream_hi = (uint32_t)(stream >> 32);
+  return r;
+}
+__device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, const DropoutRng& r) {
+  uint32_t k0 = r.seed_lo, k1 = r.seed_hi;
+  uint4 c = make_uint4(c0, c1, r.stream_lo, r.stream_hi);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ bool keep_from(uint32_t bits, float p) { return (float)(bits >> 8) * (1.0f / 16777216.0f) >= p; }
+// multiplier of element (row, col): 0 or 1 / (1 - p)
+__device__ __forceinline__ float dropout_scale(const DropoutRng& r, uint32_t row, uint32_t col) {
+  const uint4 x = philox4(col >> 2, row, r);
+  const uint32_t bits = (col & 2) ? ((col & 1) ? x.w : x.z) : ((col & 1) ? x.y : x.x);
+  return keep_from(bits, r.p) ? r.inv_keep : 0.f;
+}
+
 // ---- per-query circle geometry of the radar mask (H:543-567 / H:615-635 / H:671-693) -----------------------------
 // centre (cx, cy) in metres, box code columns 3 (log length), 6, 7 (heading terms) -> g[0..8) =
 // (cx, cy, fx, fy, rx, ry, radius, thr); thr = smallest fp32 y with sqrt_rn(y) >= radius, so that

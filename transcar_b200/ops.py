@@ -293,8 +293,13 @@ def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, wa
 ATTN_ALGOS = {"auto": _lib.TC_ATTN_AUTO, "tensor": _lib.TC_ATTN_TENSOR, "simt": _lib.TC_ATTN_SIMT, "sparse": _lib.TC_ATTN_SPARSE}
 
 
+def _set_dropout(a, dropout):
+    if dropout is not None and dropout[0] > 0:
+        a.dropout_p, a.dropout_seed, a.dropout_stream = float(dropout[0]), int(dropout[1]), int(dropout[2])
+
+
 def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_row_any=False, scale=None, out=None,
-              algo="auto"):
+              algo="auto", dropout=None):
     """q [B,Lq,E], k/v [B,Lk,E] (fp32, bf16 or fp16; views with a row stride are fine) -> out [B,Lq,E], row_any [B,Lq]
     or None.  ``out_dtype``: a torch dtype or ``"split"`` (SplitBf16)."""
     lib = _lib.load()
@@ -331,6 +336,7 @@ def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_ro
     a.out_dtype = TC_BF16X2 if isinstance(ret, SplitBf16) else _DT[out.dtype]
     a.row_any = _ptr(row_any)
     a.algo = ATTN_ALGOS[algo]
+    _set_dropout(a, dropout)          # (p, seed, stream): attention-probability dropout of the training variant
     _lib.check(_call(f"attention Lq{Lq} Lk{Lk} {algo}{' masked' if geom is not None else ''}", lib.tc_attention_fwd, C.byref(a), _stream()), "attention")
     return ret, row_any
 
@@ -531,7 +537,7 @@ def mask_grad(dy, y=None, gate=None):
     return dz
 
 
-def attention_sparse_bwd(q, k, v, dout, heads, geom, key_xy, dk, dv, scale=None):
+def attention_sparse_bwd(q, k, v, dout, heads, geom, key_xy, dk, dv, scale=None, dropout=None):
     """Backward of the masked radar attention core (fp32).  q/dout [B,Lq,E]; k/v [B,Lk,E] views; dk/dv are fp32 views of the
     same shape as k/v and are ACCUMULATED.  Returns dq [B,Lq,E]."""
     lib = _lib.load()
@@ -552,6 +558,7 @@ def attention_sparse_bwd(q, k, v, dout, heads, geom, key_xy, dk, dv, scale=None)
     a.dq, a.ld_dq = dq.data_ptr(), E
     a.dk, a.dv = dk.data_ptr(), dv.data_ptr()
     a.ld_dk, a.ld_dv, a.dk_batch_stride, a.dv_batch_stride = dk.stride(1), dv.stride(1), dk.stride(0), dv.stride(0)
+    _set_dropout(a, dropout)
     _lib.check(_call("attention_sparse_bwd", lib.tc_attention_sparse_bwd, C.byref(a), _stream()), "attention_sparse_bwd")
     return dq
 
@@ -599,7 +606,7 @@ def sample_bwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, dout,
     return d_feats, d_logits, d_ref
 
 
-def attention_dense_bwd(q, k, v, o, dout, heads, scale=None):
+def attention_dense_bwd(q, k, v, o, dout, heads, scale=None, dropout=None):
     """Backward of the mask-free attention core (fp32): q/o/dout [B,Lq,E], k/v [B,Lk,E] (strided views are fine) ->
     (dq [B,Lq,E], dk [B,Lk,E], dv [B,Lk,E]) contiguous."""
     lib = _lib.load()
@@ -620,6 +627,7 @@ def attention_dense_bwd(q, k, v, o, dout, heads, scale=None):
     a.B, a.Lq, a.Lk, a.heads, a.D = B, Lq, Lk, heads, D
     a.scale = float(scale if scale is not None else 1.0 / math.sqrt(D))
     a.dq, a.dk, a.dv, a.workspace = dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr()
+    _set_dropout(a, dropout)
     _lib.check(_call("attention_dense_bwd", lib.tc_attention_dense_bwd, C.byref(a), _stream()), "attention_dense_bwd")
     return dq, dk, dv
 
@@ -651,6 +659,20 @@ def logit(x):
 
 def sigmoid(x):
     return _pointwise(None, x, 3, "sigmoid")
+
+
+def dropout(x, p, seed, stream, residual=None, out=None):
+    """out = (residual or 0) + keep * x / (1 - p) with the regenerable Philox mask of (seed, stream); x fp32 [M,N] contiguous."""
+    lib = _lib.load()
+    x = _need(x, "x", torch.float32)
+    assert x.is_contiguous() and x.dim() == 2
+    if residual is not None:
+        residual = _need(residual, "residual", torch.float32)
+        assert residual.is_contiguous() and residual.shape == x.shape
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_call("dropout", lib.tc_dropout, _ptr(x), _ptr(residual), _ptr(out), x.shape[0], x.shape[1], float(p), int(seed),
+                     int(stream), _stream()), "dropout")
+    return out
 
 
 def add_rows(a, b, period=None, out=None):

@@ -497,6 +497,9 @@ class Detr3DHead(nn.Module):
         self.output_proj2 = nn.Linear(e, e)
         self.output_proj3 = nn.Linear(e, e)
         self._engine, self._engine_key = None, None
+        # training mode: dropout probability of the reference's modules (0.1 everywhere: nn.MultiheadAttention(dropout=0.1),
+        # rf_dropout*, mmcv attn / ffn dropout of cfg :68-80).  Set to 0.0 for deterministic gradient checks.
+        self.train_dropout, self.dropout_seed, self._train_step = 0.1, 0, 0
 
     def init_weights(self):
         self.transformer.init_weights()
@@ -563,7 +566,9 @@ class Detr3DHead(nn.Module):
         ``DecoderTrainer`` as well - sampling backward (grid_sample scatter), dense attention backward, Linear / LayerNorm
         tape - and the feature maps receive a gradient when they require one.  ``cls_branches`` / ``reg_branches`` have no
         gradient path in TransCAR (detached reference points, thresholded masks) and keep ``.grad = None``.
-        Dropout (p = 0.1 in the reference configs) is not applied: the module raises when asked to (``train_dropout``)."""
+        Dropout: ``self.train_dropout`` (0.1 like the reference's modules) is applied at the reference's sites with
+        counter-based masks (``training._TapeOps.set_dropout``).  In the frozen recipe the decoder runs in inference mode
+        (the reference keeps its dropout active even though it is frozen; its output only feeds the trained head)."""
         from .training import DecoderTrainer, RadarHeadTrainer, fusion_head_apply, radar_head_apply
         named = dict(self.named_parameters())
         unfrozen = any(p.requires_grad for n, p in named.items() if n.startswith(("transformer.", "query_embedding.")))
@@ -577,6 +582,9 @@ class Detr3DHead(nn.Module):
                                                num_layers=self.transformer.decoder.num_layers, pc_range=self.pc_range,
                                                tensor_cores=tc)
             self._trainer_key = key
+        for tr in (self._trainer, self._dec_trainer):      # fresh masks every step, regenerated (not stored) in the backward
+            tr.set_dropout(self.train_dropout, self.dropout_seed, self._train_step)
+        self._train_step += 1
         if unfrozen:
             eng = self.decoder_engine()                  # host-side input staging only (layout hand-off, metas, radar tokens)
             with torch.no_grad():

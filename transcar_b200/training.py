@@ -71,6 +71,26 @@ class _TapeOps:
             self.g[k] = self.flat_grad[off: off + t.numel()].view_as(t)
             off += t.numel()
         self.ctx = None
+        self.drop_p, self.drop_seed, self.drop_step = 0.0, 0, 0
+
+    # ------------------------------------------------------------------ dropout (training mode of the reference)
+    # Sites and probabilities of the reference: p = 0.1 on the attention probabilities and on the attention output of the
+    # decoder self-attention (mmcv MultiheadAttention, cfg :68-72) and of rf_multihead_attn* / rf_dropout2* (H:128-145,
+    # 578-581), on Detr3DCrossAtten's output (T:378), after the FFN activation and on the FFN output (mmcv FFN ffn_dropout /
+    # rf_dropout*, rf_dropout3*: H:583-585).  Masks are regenerated from (seed, stream) in the backward pass; stream =
+    # step * 1024 + layer * 8 + kind with layers 0-5 = decoder, 6-8 = radar, kind: 0 attention probabilities,
+    # 1 attention output, 2 cross-attention output, 3 FFN hidden, 4 FFN output.
+    KIND_PROBS, KIND_ATTN_OUT, KIND_CROSS_OUT, KIND_FFN_HIDDEN, KIND_FFN_OUT = 0, 1, 2, 3, 4
+
+    def set_dropout(self, p=0.0, seed=0, step=0):
+        self.drop_p, self.drop_seed, self.drop_step = float(p), int(seed), int(step)
+
+    def _stream(self, layer, kind):
+        return self.drop_step * 1024 + layer * 8 + kind
+
+    def _drop_arg(self, layer, kind):
+        """(p, seed, stream) for the attention kernels, or None when dropout is off."""
+        return (self.drop_p, self.drop_seed, self._stream(layer, kind)) if self.drop_p > 0 else None
 
     # ------------------------------------------------------------------ GEMM plumbing
     def _wsplit(self, wkey, w_rows, W, transposed):
@@ -82,22 +102,33 @@ class _TapeOps:
         return t
 
     # ------------------------------------------------------------------ differentiable pieces (forward records a tape)
-    def _linear(self, tape, x, wkey, bkey, relu=False, residual=None, gate=None, w_rows=None, residual2=None):
+    def _linear(self, tape, x, wkey, bkey, relu=False, residual=None, gate=None, w_rows=None, residual2=None, drop=None):
         """y = [relu]( gate * (x W^T + b) + residual + residual2 ).  ``w_rows`` selects a row range of a packed
-        weight/bias.  The residual terms pass their gradient through unchanged (the caller routes it)."""
+        weight/bias.  The residual terms pass their gradient through unchanged (the caller routes it).
+        ``drop = (layer, kind)``: dropout on the Linear's (activated, gated) output BEFORE the residuals are added."""
         W, b = self.p[wkey], self.p[bkey]
         if w_rows is not None:
             W, b = W[w_rows[0]:w_rows[1]], b[w_rows[0]:w_rows[1]]
+        if drop is not None and self.drop_p > 0:
+            stream = self._stream(*drop)
+            t = self._linear([], x, wkey, bkey, relu=relu, gate=gate, w_rows=w_rows)
+            y = ops.dropout(t, self.drop_p, self.drop_seed, stream, residual=residual)
+            if residual2 is not None:
+                y = ops.add_rows(y, residual2.contiguous(), y.shape[0], out=y)
+            tape.append(("linear", x, wkey, bkey, w_rows, t if relu else None, gate, stream))
+            return y
         if self.tc and x.shape[1] % 64 == 0:
             y, _ = ops.linear(ops.cast_split(x), self._wsplit(wkey, w_rows, W, False), b, relu=relu, residual=residual,
                               residual2=residual2, row_gate=gate)
         else:               # K = 3 / 36 (raw radar fields, reference points): exact fp32 CUDA-core path
             y, _ = ops.linear(x, W, b, relu=relu, residual=residual, residual2=residual2, row_gate=gate)
-        tape.append(("linear", x, wkey, bkey, w_rows, y if relu else None, gate))
+        tape.append(("linear", x, wkey, bkey, w_rows, y if relu else None, gate, None))
         return y
 
     def _linear_bwd(self, rec, dy, dx_accum=None, need_dx=True):
-        _, x, wkey, bkey, w_rows, y_relu, gate = rec
+        _, x, wkey, bkey, w_rows, y_relu, gate, stream = rec
+        if stream is not None:               # same mask as the forward, regenerated
+            dy = ops.dropout(dy.contiguous(), self.drop_p, self.drop_seed, stream)
         if y_relu is not None or gate is not None:
             dy = ops.mask_grad(dy, y=y_relu, gate=gate)
         W, gW, gb = self.p[wkey], self.g[wkey], self.g[bkey]
@@ -183,12 +214,15 @@ class RadarHeadTrainer(_TapeOps):
             kv = self._linear(tape, kvfeat_sum, mha + ".in_proj_weight", mha + ".in_proj_bias", w_rows=(C, 3 * C))
             kv3 = kv.view(B, R, 2 * C)
             att, row_any = ops.attention(q.view(B, Q, C), kv3[:, :, :C], kv3[:, :, C:], self.heads, geom=geom, key_xy=key_xy,
-                                         want_row_any=True, algo="sparse")
+                                         want_row_any=True, algo="sparse", dropout=self._drop_arg(6 + li, self.KIND_PROBS))
             gate = row_any.view(M)
-            z2 = self._linear(tape, att.view(M, C), mha + ".out_proj.weight", mha + ".out_proj.bias", residual=x, gate=gate)
+            z2 = self._linear(tape, att.view(M, C), mha + ".out_proj.weight", mha + ".out_proj.bias", residual=x, gate=gate,
+                              drop=(6 + li, self.KIND_ATTN_OUT))
             x2 = self._ln(tape, z2, "rf_norm2" + s)
-            h = self._linear(tape, x2, "rf_linear1" + s + ".weight", "rf_linear1" + s + ".bias", relu=True)
-            z3 = self._linear(tape, h, "rf_linear2" + s + ".weight", "rf_linear2" + s + ".bias", residual=x2)
+            h = self._linear(tape, x2, "rf_linear1" + s + ".weight", "rf_linear1" + s + ".bias", relu=True,
+                             drop=(6 + li, self.KIND_FFN_HIDDEN))
+            z3 = self._linear(tape, h, "rf_linear2" + s + ".weight", "rf_linear2" + s + ".bias", residual=x2,
+                              drop=(6 + li, self.KIND_FFN_OUT))
             x3 = self._ln(tape, z3, "rf_norm3" + s)
             n_trunk = len(tape)
             c = self._ln(tape, self._linear(tape, x3, f"final_cls{m}.0.weight", f"final_cls{m}.0.bias"), f"final_cls{m}.1", relu=True)
@@ -246,7 +280,8 @@ class RadarHeadTrainer(_TapeOps):
             kv3 = L["kv"].view(B, R, 2 * C)
             dkv = torch.zeros((B, R, 2 * C), device=dev, dtype=torch.float32)
             dq = ops.attention_sparse_bwd(L["q"].view(B, Q, C), kv3[:, :, :C], kv3[:, :, C:], datt.view(B, Q, C), self.heads,
-                                          L["geom"], ctx["key_xy"], dkv[:, :, :C], dkv[:, :, C:])
+                                          L["geom"], ctx["key_xy"], dkv[:, :, :C], dkv[:, :, C:],
+                                          dropout=self._drop_arg(6 + li, self.KIND_PROBS))
             d_kvfeat = self._linear_bwd(tape[1], dkv.view(B * R, 2 * C), dx_accum=d_kvfeat)
             dx_next = self._linear_bwd(tape[0], dq.view(M, C), dx_accum=dz2, need_dx=li > 0 or need_dx0)   # + skip z2 = x + ...
         # ---- radar encoders: kvfeat = pos + relu(feat)
@@ -270,7 +305,7 @@ class DecoderTrainer(_TapeOps):
     grid_sample scatter (``tc_sample_bwd``) and the dense self-attention backward (``tc_attention_dense_bwd``) - plus the
     Linear / LayerNorm tape shared with the radar head.  Reference points are detached between layers (T:203), so only layer 0
     sends gradient into ``transformer.reference_points`` (through the sampling grid and the position encoder); the
-    refinement branches themselves run without a tape.  Dropout is not applied (identity in eval; see ``forward_train``)."""
+    refinement branches themselves run without a tape.  Dropout: see ``_TapeOps.set_dropout``."""
 
     def __init__(self, params, num_query, num_heads=8, num_layers=6, pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0),
                  tensor_cores=True):
@@ -309,8 +344,10 @@ class DecoderTrainer(_TapeOps):
             q = self._linear(tape, xp, mha + "in_proj_weight", mha + "in_proj_bias", w_rows=(0, C))
             k = self._linear(tape, xp, mha + "in_proj_weight", mha + "in_proj_bias", w_rows=(C, 2 * C))
             v = self._linear(tape, x, mha + "in_proj_weight", mha + "in_proj_bias", w_rows=(2 * C, 3 * C))
-            o, _ = ops.attention(q.view(B, Q, C), k.view(B, Q, C), v.view(B, Q, C), self.heads, algo="simt")
-            z = self._linear(tape, o.view(M, C), mha + "out_proj.weight", mha + "out_proj.bias", residual=x)
+            o, _ = ops.attention(q.view(B, Q, C), k.view(B, Q, C), v.view(B, Q, C), self.heads, algo="simt",
+                                 dropout=self._drop_arg(l, self.KIND_PROBS))
+            z = self._linear(tape, o.view(M, C), mha + "out_proj.weight", mha + "out_proj.bias", residual=x,
+                             drop=(l, self.KIND_ATTN_OUT))
             x1 = self._ln(tape, z, pre + "norms.0")
             # ---- Detr3DCrossAtten (T:302-378): residual = x1 (quirk Q1), logits from x1 + query_pos
             xp1 = ops.add_rows(x1, pos_q, Q)
@@ -321,11 +358,14 @@ class DecoderTrainer(_TapeOps):
                           ca + "position_encoder.1", relu=True)
             pf = self._ln(tape, self._linear(tape, pe, ca + "position_encoder.3.weight", ca + "position_encoder.3.bias"),
                           ca + "position_encoder.4", relu=True)
-            z2 = self._linear(tape, s.view(M, C), ca + "output_proj.weight", ca + "output_proj.bias", residual=x1, residual2=pf)
+            z2 = self._linear(tape, s.view(M, C), ca + "output_proj.weight", ca + "output_proj.bias", residual=x1, residual2=pf,
+                              drop=(l, self.KIND_CROSS_OUT))
             x2 = self._ln(tape, z2, pre + "norms.1")
             # ---- FFN
-            h = self._linear(tape, x2, pre + "ffns.0.layers.0.0.weight", pre + "ffns.0.layers.0.0.bias", relu=True)
-            z3 = self._linear(tape, h, pre + "ffns.0.layers.1.weight", pre + "ffns.0.layers.1.bias", residual=x2)
+            h = self._linear(tape, x2, pre + "ffns.0.layers.0.0.weight", pre + "ffns.0.layers.0.0.bias", relu=True,
+                             drop=(l, self.KIND_FFN_HIDDEN))
+            z3 = self._linear(tape, h, pre + "ffns.0.layers.1.weight", pre + "ffns.0.layers.1.bias", residual=x2,
+                              drop=(l, self.KIND_FFN_OUT))
             x3 = self._ln(tape, z3, pre + "norms.2")
             ctx["layers"].append(dict(tape=tape, q=q, k=k, v=v, o=o, ref=ref, logits=logits))
             # ---- iterative refinement (T:190-203), detached
@@ -374,7 +414,7 @@ class DecoderTrainer(_TapeOps):
             dz = self._ln_bwd(t[4], dx1)
             do = self._linear_bwd(t[3], dz)
             dq, dk, dv = ops.attention_dense_bwd(Lc["q"].view(B, Q, C), Lc["k"].view(B, Q, C), Lc["v"].view(B, Q, C), Lc["o"],
-                                                 do.view(B, Q, C), self.heads)
+                                                 do.view(B, Q, C), self.heads, dropout=self._drop_arg(l, self.KIND_PROBS))
             dxp = self._linear_bwd(t[0], dq.view(M, C))
             dxp = self._linear_bwd(t[1], dk.view(M, C), dx_accum=dxp)
             ops.add_rows(dpos, dxp, M, out=dpos)
