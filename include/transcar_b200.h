@@ -82,6 +82,10 @@ TC_API uint64_t tc_launch_count(void);
  * the un-masked return value of the reference's free function feature_sampling (T:381-422); the fused hot path
  * (Detr3DCrossAtten) multiplies by the mask and therefore never sets it. */
 #define TC_SAMPLE_ALL_CAMS 1
+/* TC_SAMPLE_WEIGHTS_GIVEN = attn_logits already holds the per-(camera, level) weights (no sigmoid is applied): how
+ * num_points > 1 configurations are served - the reference samples ONE point and broadcasts it against num_points weights
+ * (T:346-373), i.e. the effective weight is sum_p sigmoid(logit[cam, p, level]). */
+#define TC_SAMPLE_WEIGHTS_GIVEN 2
 typedef struct {
   const void* feat[TC_MAX_LEVELS];
   int32_t H[TC_MAX_LEVELS];
@@ -221,6 +225,10 @@ typedef struct {
   /* training variant: dropout on the attention probabilities (nn.MultiheadAttention(dropout=0.1), H:128 / mmcv attn_drop),
    * mask = tc_dropout's for the logical [B*heads*Lq, Lk] tensor, row = (b * heads + h) * Lq + q.  SIMT and sparse paths. */
   float dropout_p; uint64_t dropout_seed; uint64_t dropout_stream;
+  /* generic masks of nn.MultiheadAttention (the mmcv wrapper's attn_mask / key_padding_mask arguments; never used by the
+   * TransCAR configs, served by the SIMT path): attn_blocked [Lq, Lk] uint8 shared by all samples and heads,
+   * key_blocked [B, Lk] uint8; 1 = the key is not attended.  Either may be NULL. */
+  const uint8_t* attn_blocked; const uint8_t* key_blocked;
 } tc_attention_args;
 TC_API int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream);
 

@@ -142,7 +142,8 @@ def sampled_sum(sd, prefix, q_plus_pos, mlvl_feats, ref, img_metas):
     B, Q, _ = q_plus_pos.shape
     n_levels = len(mlvl_feats)
     n_cams = mlvl_feats[0].shape[1]
-    aw = lin(sd, prefix + ".attention_weights", q_plus_pos).view(B, 1, Q, n_cams, 1, n_levels)
+    # num_points (1 in the TransCAR configs, 5 by default) is whatever the Linear's width implies: T:362-365
+    aw = lin(sd, prefix + ".attention_weights", q_plus_pos).view(B, 1, Q, n_cams, -1, n_levels)
     ref3d, out, mask = feature_sampling(mlvl_feats, ref, img_metas)
     out = torch.nan_to_num(out, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
     w = aw.sigmoid() * mask

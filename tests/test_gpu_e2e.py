@@ -257,6 +257,44 @@ def test_cross_atten_module_dropin():
     assert torch.equal(mod.last_mask.bool().cpu(), mask[:, 0, :, :, 0, 0])
 
 
+def test_cross_atten_num_points_5_and_mmcv_attention_masks():
+    """Boundary completeness: (a) `Detr3DCrossAtten(num_points=5)` - the reference default - one sampled point broadcast
+    against five weights (T:346-373); (b) the mmcv `MultiheadAttention` wrapper with `attn_mask` / `key_padding_mask`
+    against torch's nn.MultiheadAttention."""
+    from transcar_b200 import plugin
+    Q, B = 96, 2
+    gen = torch.Generator().manual_seed(31)
+    mod = plugin.ATTENTION.build(dict(type="Detr3DCrossAtten", pc_range=synthetic.PC_RANGE, num_points=5, embed_dims=256))
+    with torch.no_grad():
+        mod.attention_weights.weight.copy_(torch.randn(mod.attention_weights.weight.shape, generator=gen) * 0.05)
+    mod = mod.cuda().eval()
+    pre = "x"
+    sd = {pre + "." + k: v.detach() for k, v in mod.state_dict().items()}      # oracle on the GPU (ATen's CUDA grid_sample)
+    feats = synthetic.make_feats(6, B, "tiny", smooth=True)
+    metas = synthetic.make_img_metas(B, seed=6)
+    query, pos = torch.randn((Q, B, 256), generator=gen), torch.randn((Q, B, 256), generator=gen)
+    ref = torch.rand((B, Q, 3), generator=gen)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = O.cross_atten(sd, pre, query.cuda(), pos.cuda(), [f.cuda() for f in feats], ref.cuda(), metas)
+        got = mod(query.cuda(), None, [f.cuda() for f in feats], query_pos=pos.cuda(), reference_points=ref.cuda(), img_metas=metas)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=4e-5)
+    # ---- (b)
+    att = plugin.ATTENTION.build(dict(type="MultiheadAttention", embed_dims=256, num_heads=8, dropout=0.1)).cuda().eval()
+    ref_mha = torch.nn.MultiheadAttention(256, 8).cuda().eval()
+    ref_mha.load_state_dict(att.attn.state_dict())
+    Lq, Lk = 70, 90
+    q, k = torch.randn((Lq, B, 256), generator=gen).cuda(), torch.randn((Lk, B, 256), generator=gen).cuda()
+    amask = torch.rand((Lq, Lk), generator=gen).cuda() < 0.3
+    amask[:, 0] = False                                           # every row keeps at least one key
+    kpm = torch.rand((B, Lk), generator=gen).cuda() < 0.2
+    kpm[:, 0] = False
+    with torch.no_grad():
+        got = att(q, k, k, attn_mask=amask, key_padding_mask=kpm)
+        want = q + ref_mha(q, k, k, attn_mask=amask, key_padding_mask=kpm)[0]
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-5)
+
+
 def test_transformer_module_dropin():
     """`Detr3DTransformer.forward(mlvl_feats, query_embed, reg_branches, img_metas=...)` return contract."""
     g, head, sd, feats, metas = build("tiny", "fp32")

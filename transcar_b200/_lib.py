@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libtranscar_b200.so")
 TC_F32, TC_BF16, TC_BF16X2, TC_F16 = 0, 1, 2, 3
 TC_MAX_LEVELS, TC_MAX_CAMS = 4, 8
 ABI_VERSION = 5
-TC_SAMPLE_ALL_CAMS = 1
+TC_SAMPLE_ALL_CAMS, TC_SAMPLE_WEIGHTS_GIVEN = 1, 2
 TC_TAIL_NONE, TC_TAIL_REF_UPDATE, TC_TAIL_BOX = 0, 1, 2
 TC_ATTN_AUTO, TC_ATTN_TENSOR, TC_ATTN_SIMT, TC_ATTN_SPARSE = 0, 1, 2, 3
 
@@ -67,7 +67,8 @@ class AttentionArgs(C.Structure):
                 ("geom", _vp), ("key_xy", _vp),
                 ("out", _vp), ("ldo", _i64), ("out_dtype", _i32),
                 ("row_any", _vp), ("algo", _i32),
-                ("dropout_p", _f32), ("dropout_seed", C.c_uint64), ("dropout_stream", C.c_uint64)]
+                ("dropout_p", _f32), ("dropout_seed", C.c_uint64), ("dropout_stream", C.c_uint64),
+                ("attn_blocked", _vp), ("key_blocked", _vp)]
 
 
 class RadarGeometryArgs(C.Structure):

@@ -22,6 +22,7 @@ struct AttnParams {
   void* out; long long ldo;
   uint8_t* row_any;
   DropoutRng rng;          // p == 0: no dropout
+  const uint8_t* attn_blocked; const uint8_t* key_blocked;      // generic nn.MultiheadAttention masks (may be NULL)
 };
 
 template <bool kBf16>
@@ -120,6 +121,8 @@ __global__ void __launch_bounds__(kRows) attention_simt_kernel(const AttnParams 
         const int jj = j0 + j;
         bool a = jj < nk;
         if (kMask && a) a = radar_allowed(cc, cf, cr, radius, Kx[jj], Ky[jj], Kn[jj]);
+        if (a && p.attn_blocked) a = p.attn_blocked[(long long)row * p.Lk + k0 + jj] == 0;
+        if (a && p.key_blocked) a = p.key_blocked[(long long)b * p.Lk + k0 + jj] == 0;
         ok[j] = a;
         any |= a;
       }
@@ -236,6 +239,7 @@ int attention_simt_launch(const tc_attention_args* a, cudaStream_t s) {
   p.scale = a->scale; p.geom = a->geom; p.key_xy = a->key_xy;
   p.out = a->out; p.ldo = a->ldo; p.row_any = a->row_any;
   p.rng = make_rng(a->dropout_p, a->dropout_seed, a->dropout_stream);
+  p.attn_blocked = a->attn_blocked; p.key_blocked = a->key_blocked;
   dim3 grid((a->Lq + kRows - 1) / kRows, a->heads, a->B);
   const bool bi = a->qkv_dtype == TC_BF16, bo = a->out_dtype == TC_BF16, mk = a->geom != nullptr;
 #define TC_ATTN_LAUNCH(BI, BO, MK) attention_simt_kernel<BI, BO, MK><<<grid, kRows, 0, s>>>(p)

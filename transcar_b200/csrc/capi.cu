@@ -132,6 +132,11 @@ extern "C" int tc_attention_fwd(const tc_attention_args* a, tc_stream_t stream) 
   TC_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, TC_ERR_SHAPE, "tc_attention_fwd: dropout_p must be in [0, 1)");
   if (a->B == 0 || a->Lq == 0) return TC_OK;
   cudaStream_t s = as_stream(stream);
+  if (a->attn_blocked || a->key_blocked) {      // generic dense masks: CUDA-core path only
+    TC_REQUIRE(a->algo == TC_ATTN_AUTO || a->algo == TC_ATTN_SIMT, TC_ERR_SHAPE, "tc_attention_fwd: attn_blocked / key_blocked need the SIMT path");
+    TC_REQUIRE(a->qkv_dtype != TC_F16 && a->out_dtype != TC_BF16X2, TC_ERR_DTYPE, "tc_attention_fwd: attn_blocked / key_blocked take fp32 / bf16 operands");
+    return attention_simt_launch(a, s);
+  }
   if (a->dropout_p > 0.f) {        // training variant: probability dropout lives in the fp32 kernels only
     TC_REQUIRE(a->algo != TC_ATTN_TENSOR && a->qkv_dtype != TC_F16 && a->out_dtype != TC_BF16X2, TC_ERR_DTYPE,
                "tc_attention_fwd: dropout is supported on the SIMT and sparse paths");

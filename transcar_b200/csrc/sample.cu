@@ -54,6 +54,7 @@ struct SampleParams {
   void* out;
   uint8_t* mask;
   int all_cams;            // TC_SAMPLE_ALL_CAMS
+  int weights_given;       // TC_SAMPLE_WEIGHTS_GIVEN
 };
 
 // ATen grid_sampler_unnormalize, align_corners=False: ((g + 1) * size - 1) / 2.
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(kWarps * 32, kWarps <= 6 ? 2 : 1) sample_kerne
     const unsigned vset = __ballot_sync(0xffffffffu, valid || (p.all_cams && lane < p.N));
 
     // -- sigmoid(attention logits): lane i < N*4 holds weight i = cam*4 + level ----------------------
-    const float wgt = (lane < p.N * 4) ? sigmoid_f32(cur.logit) : 0.f;
+    const float wgt = (lane < p.N * 4) ? (p.weights_given ? cur.logit : sigmoid_f32(cur.logit)) : 0.f;
 
     // -- next query's inputs: issued now, consumed in the next iteration ------------------------------
     if (next < range_end) fetch_query(p, next, lane, nxt);
@@ -404,6 +405,7 @@ extern "C" int tc_sample_fwd(const tc_sample_args* a, tc_stream_t stream) {
   p.inv_w = 1.0f / a->img_w; p.inv_h = 1.0f / a->img_h; p.inv_q = 1.0f / (float)a->Q;
   p.out = a->out; p.mask = a->mask;
   p.all_cams = (a->flags & TC_SAMPLE_ALL_CAMS) ? 1 : 0;
+  p.weights_given = (a->flags & TC_SAMPLE_WEIGHTS_GIVEN) ? 1 : 0;
   // persistent warps, one CTA per SM; each CTA hands its range of queries out to its warps dynamically
   static int sm_count = 0;
   if (sm_count == 0) {

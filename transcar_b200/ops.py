@@ -123,7 +123,7 @@ def to_channels_last(f, dtype=None):
 
 
 def sample_fwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, out_dtype=torch.float32,
-               want_mask=False, out=None, all_cams=False):
+               want_mask=False, out=None, all_cams=False, weights_given=False):
     """feats: 4 x logical [B,N,C,H,W] channels-last; ref [B,Q,3]; lidar2img [B,N,4,4]; attn_logits [B,Q,N*L].
     ``out_dtype``: torch.float32 / torch.bfloat16 / ``"split"`` (SplitBf16 [B,Q,C]).
     Returns (out [B,Q,C], mask [B,Q,N] uint8 or None)."""
@@ -163,7 +163,7 @@ def sample_fwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, out_d
     a.img_w, a.img_h = float(img_w), float(img_h)
     a.out = out.data_ptr()
     a.mask = mask.data_ptr() if mask is not None else None
-    a.flags = _lib.TC_SAMPLE_ALL_CAMS if all_cams else 0
+    a.flags = (_lib.TC_SAMPLE_ALL_CAMS if all_cams else 0) | (_lib.TC_SAMPLE_WEIGHTS_GIVEN if weights_given else 0)
     _lib.check(_call("sample", lib.tc_sample_fwd, C.byref(a), _stream()), "sample_fwd")
     return ret, mask
 
@@ -299,7 +299,7 @@ def _set_dropout(a, dropout):
 
 
 def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_row_any=False, scale=None, out=None,
-              algo="auto", dropout=None):
+              algo="auto", dropout=None, attn_blocked=None, key_blocked=None):
     """q [B,Lq,E], k/v [B,Lk,E] (fp32, bf16 or fp16; views with a row stride are fine) -> out [B,Lq,E], row_any [B,Lq]
     or None.  ``out_dtype``: a torch dtype or ``"split"`` (SplitBf16)."""
     lib = _lib.load()
@@ -337,6 +337,14 @@ def attention(q, k, v, heads, *, geom=None, key_xy=None, out_dtype=None, want_ro
     a.row_any = _ptr(row_any)
     a.algo = ATTN_ALGOS[algo]
     _set_dropout(a, dropout)          # (p, seed, stream): attention-probability dropout of the training variant
+    if attn_blocked is not None:      # [Lq, Lk] uint8 / bool, 1 = blocked (nn.MultiheadAttention attn_mask)
+        attn_blocked = _need(attn_blocked.to(torch.uint8), "attn_blocked", torch.uint8).contiguous()
+        assert attn_blocked.shape == (Lq, Lk)
+        a.attn_blocked = attn_blocked.data_ptr()
+    if key_blocked is not None:       # [B, Lk] (key_padding_mask)
+        key_blocked = _need(key_blocked.to(torch.uint8), "key_blocked", torch.uint8).contiguous()
+        assert key_blocked.shape == (B, Lk)
+        a.key_blocked = key_blocked.data_ptr()
     _lib.check(_call(f"attention Lq{Lq} Lk{Lk} {algo}{' masked' if geom is not None else ''}", lib.tc_attention_fwd, C.byref(a), _stream()), "attention")
     return ret, row_any
 

@@ -98,8 +98,8 @@ class MultiheadAttention(nn.Module):
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
                 key_padding_mask=None, **kwargs):
         _no_grad_required(self)
-        if attn_mask is not None or key_padding_mask is not None:
-            raise NotImplementedError("transcar_b200.MultiheadAttention: dense masks are not part of the hot path")
+        if attn_mask is not None and (attn_mask.dtype.is_floating_point or attn_mask.dim() != 2):
+            raise NotImplementedError("transcar_b200.MultiheadAttention: attn_mask must be a 2-D bool / uint8 mask [Lq, Lk]")
         key = query if key is None else key
         value = key if value is None else value
         identity = query if identity is None else identity
@@ -120,7 +120,7 @@ class MultiheadAttention(nn.Module):
         q = proj(query, query_pos, 0, E)
         k = proj(key, key_pos, E, 2 * E)
         v = proj(value, None, 2 * E, 3 * E)
-        att, _ = ops.attention(q, k, v, self.num_heads)
+        att, _ = ops.attention(q, k, v, self.num_heads, attn_blocked=attn_mask, key_blocked=key_padding_mask)
         out, _ = ops.linear(att.view(-1, E), self.attn.out_proj.weight, self.attn.out_proj.bias,
                             residual=identity.permute(1, 0, 2).reshape(-1, E).contiguous())
         return out.view(B, Lq, E).permute(1, 0, 2)
@@ -183,8 +183,6 @@ class Detr3DCrossAtten(nn.Module):
         super().__init__()
         if embed_dims % num_heads != 0:
             raise ValueError(f"embed_dims must be divisible by num_heads, but got {embed_dims} and {num_heads}")
-        if num_points != 1:
-            raise NotImplementedError("transcar_b200.Detr3DCrossAtten: only num_points=1 (the TransCAR configs)")
         self.embed_dims, self.num_heads, self.num_levels = embed_dims, num_heads, num_levels
         self.num_points, self.num_cams, self.im2col_step = num_points, num_cams, im2col_step
         self.pc_range, self.norm_cfg, self.init_cfg, self.batch_first = pc_range, norm_cfg, init_cfg, batch_first
@@ -219,8 +217,16 @@ class Detr3DCrossAtten(nn.Module):
         ref = reference_points.contiguous().float()
         l2i = _lidar2img_tensor(img_metas, query.device).view(B, self.num_cams, 4, 4)
         shape0 = img_metas[0]["img_shape"][0]
-        s, mask = ops.sample_fwd(feats, ref, l2i, aw.view(B, Q, -1), self.pc_range, shape0[1], shape0[0],
-                                 out_dtype=torch.float32, want_mask=True)
+        if self.num_points == 1:
+            s, mask = ops.sample_fwd(feats, ref, l2i, aw.view(B, Q, -1), self.pc_range, shape0[1], shape0[0],
+                                     out_dtype=torch.float32, want_mask=True)
+        else:
+            # num_points > 1 (the reference default is 5; the TransCAR configs use 1): ONE point is sampled and broadcast
+            # against num_points weights (T:346-373), so the effective weight of a (camera, level) is
+            # sum_p sigmoid(logit[cam, p, level]) - tensor glue, then the kernel takes the weights as given
+            w = aw.view(B, Q, self.num_cams, self.num_points, self.num_levels).sigmoid().sum(3)
+            s, mask = ops.sample_fwd(feats, ref, l2i, w.reshape(B, Q, -1).contiguous(), self.pc_range, shape0[1], shape0[0],
+                                     out_dtype=torch.float32, want_mask=True, weights_given=True)
         self.last_mask = mask                                           # [B,Q,N] uint8 (T:400-409)
         pe = self.position_encoder
         p1, _ = ops.point_embed(ref.view(B * Q, 3), pe[0].weight, pe[0].bias, pe[1].weight, pe[1].bias, logit_input=True)
