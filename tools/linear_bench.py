@@ -47,4 +47,4 @@ with torch.no_grad():
     for M, N, K, kind in SHAPES:
         t1, t3 = run("bf16", M, N, K, kind), run("x3", M, N, K, kind)
         gf = 2 * M * N * K / 1e9
-        print(f"M{M:6d} N{N:5d} K{K:4d} {kind:8s}  bf16 {t1:6.2f} us ({gf / t1 * 1e-3:6.1f} TF/s)   bf16x3 {t3:6.2f} us ({gf / t3 * 1e-3:6.1f} TF/s algorithmic)  x{t3 / t1:.2f}", flush=True)
+        print(f"M{M:6d} N{N:5d} K{K:4d} {kind:8s}  bf16 {t1:6.2f} us ({gf / t1 * 1e3:6.1f} TF/s)   bf16x3 {t3:6.2f} us ({gf / t3 * 1e3:6.1f} TF/s algorithmic)  x{t3 / t1:.2f}", flush=True)

@@ -10,7 +10,7 @@ cfg = synthetic.head_config(900); cfg["precision"] = precision
 head = plugin.build_head(cfg); head.load_state_dict(synthetic.make_state_dict(0, 900)); head = head.cuda().eval()
 eng = head.engine()
 feats = [f.to(torch.bfloat16).cuda().permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
-         for f in synthetic.make_feats(0, B, "res101", smooth=False)]
+         for f in synthetic.make_feats(0, B, "res101", smooth=True)]
 prepared = eng.prepare_inputs(feats, synthetic.make_img_metas(B, seed=0))
 for _ in range(3):
     eng.forward_prepared(prepared)
