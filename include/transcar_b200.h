@@ -34,7 +34,7 @@ extern "C" {
 #define TC_API
 #endif
 
-#define TC_ABI_VERSION 5
+#define TC_ABI_VERSION 6
 #define TC_MAX_LEVELS 4
 #define TC_MAX_CAMS 8
 
@@ -62,6 +62,10 @@ TC_API const char* tc_last_error_string(void);
 TC_API int tc_check_device(void);
 /* Number of kernels this library has enqueued from the calling process since load (bench evidence). */
 TC_API uint64_t tc_launch_count(void);
+/* Profiling hook (tools/linear_trace.py): every CTA of the following tensor-core tc_linear launches writes 16 uint64
+ * timestamps (globaltimer ns / clock64 cycles at its phase boundaries, SM id) into `device_buf`, one record per CTA in launch
+ * order, until `records` are used up.  NULL / 0 switches it off (the default; the kernels then do no extra work). */
+TC_API int tc_debug_trace(uint64_t* device_buf, int64_t records);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  fused camera sampling.   Replaces T:381-422 (feature_sampling: projection through lidar2img,
@@ -144,6 +148,10 @@ TC_API int tc_nchw_to_nhwc(const float* src, void* dst, int32_t dst_dtype, int32
  * out16_dtype selects the 16-bit output format: 0 or TC_BF16 -> bf16 [M, N];  TC_BF16X2 -> split bf16 [M, 2N]
  * (hi at column n, lo at column N + n; ld_out_bf16 >= 2N) - the A operand of the next bf16x3 Linear;  TC_F16 -> IEEE
  * half [M, N], saturated to +-65504 - the q/k/v operands of the dense attention core in bf16x3 mode.
+ * w_static != 0 promises that W is not written by any earlier launch still in flight on the stream (a weight, not an
+ * activation): the tensor-core kernel then fetches the first W tiles BEFORE it waits for its predecessor (programmatic
+ * dependent launch), hiding their latency behind the previous kernel's tail.  Leave 0 when W is produced on the stream
+ * (the dgrad / wgrad GEMMs of the training variant).
  */
 enum { TC_TAIL_NONE = 0, TC_TAIL_REF_UPDATE = 1, TC_TAIL_BOX = 2 };
 typedef struct {
@@ -168,6 +176,7 @@ typedef struct {
   int32_t tail_xy_col, tail_z_col, tail_from_norm;
   float tail_pc_range[6];
   float tail_r_lo, tail_r_hi;
+  int32_t w_static;                               /* W is a parameter no earlier launch of the stream writes (see above) */
 } tc_linear_args;
 TC_API int tc_linear(const tc_linear_args* a, tc_stream_t stream);
 

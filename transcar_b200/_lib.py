@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtranscar_b200.so")
 
 TC_F32, TC_BF16, TC_BF16X2, TC_F16 = 0, 1, 2, 3
 TC_MAX_LEVELS, TC_MAX_CAMS = 4, 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 TC_SAMPLE_ALL_CAMS, TC_SAMPLE_WEIGHTS_GIVEN = 1, 2
 TC_TAIL_NONE, TC_TAIL_REF_UPDATE, TC_TAIL_BOX = 0, 1, 2
 TC_ATTN_AUTO, TC_ATTN_TENSOR, TC_ATTN_SIMT, TC_ATTN_SPARSE = 0, 1, 2, 3
@@ -48,7 +48,7 @@ class LinearArgs(C.Structure):
                 ("out16_dtype", _i32),
                 ("tail", _i32), ("tail_in", _vp), ("ld_tail_in", _i64), ("tail_ref_out", _vp), ("tail_geom_out", _vp),
                 ("tail_xy_col", _i32), ("tail_z_col", _i32), ("tail_from_norm", _i32),
-                ("tail_pc_range", _f32 * 6), ("tail_r_lo", _f32), ("tail_r_hi", _f32)]
+                ("tail_pc_range", _f32 * 6), ("tail_r_lo", _f32), ("tail_r_hi", _f32), ("w_static", _i32)]
 
 
 class PointEmbedArgs(C.Structure):
@@ -157,6 +157,7 @@ SYMBOLS = {
     "tc_last_error_string": (C.c_char_p, []),
     "tc_check_device": (C.c_int, []),
     "tc_launch_count": (C.c_uint64, []),
+    "tc_debug_trace": (C.c_int, [_vp, _i64]),
     "tc_sample_fwd": (C.c_int, [C.POINTER(SampleArgs), _vp]),
     "tc_nchw_to_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tc_linear": (C.c_int, [C.POINTER(LinearArgs), _vp]),

@@ -35,12 +35,13 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
+    flags = FLAGS + (["-DTC_TRACE_BUILD"] if os.environ.get("TC_TRACE_BUILD") else [])   # tools/linear_trace.py marks
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC, *FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        cmd = [NVCC, *flags, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

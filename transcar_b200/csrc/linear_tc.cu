@@ -18,7 +18,8 @@
 //     stores; fp32 and / or a 16-bit copy (bf16, split bf16 for the next bf16x3 GEMM, or fp16 for the attention core).
 //     LayerNorm needs the whole row (N = 64, 128 or 256): the 1, 2 or 4 CTAs that share a row block form a
 //     thread-block cluster and exchange per-row (sum, sum of squares) through distributed shared memory.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (one
+// accumulator row x 32 columns per thread).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -36,10 +37,12 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 64;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;               // producer warp, MMA warp, eight epilogue warps
+constexpr int HN = 32;                      // columns per epilogue thread (two threads share an accumulator row)
 constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kBBytes = BN * BK * 2;
 constexpr int kMaxCluster = 4;                        // LayerNorm rows span at most 4 CTAs (N <= 256)
+constexpr int kSlots = 2 * kMaxCluster;               // statistics contributors per row: (CTA, column half)
 // shared-memory carve-up per operand mode.  after the ring: barriers (full, empty, acc, init) + tmem slot, column
 // vectors (bias, gamma, beta), LN partials
 // (Measured and rejected: a 4-stage, 192 KB ring for split-mode grids of at most one CTA per SM - N <= 64, 57 CTAs at
@@ -52,7 +55,7 @@ struct Cfg {
   static constexpr uint32_t kOffBars = kStages * kStageBytes;
   static constexpr uint32_t kOffVec = kOffBars + 128;
   static constexpr uint32_t kOffPart = kOffVec + 3 * BN * 4;
-  static constexpr uint32_t kSmemUsed = kOffPart + kMaxCluster * BM * 8;
+  static constexpr uint32_t kSmemUsed = kOffPart + 2 * kMaxCluster * BM * 8;       // LN partials: one slot per (CTA, column half)
   static constexpr size_t kSmemBytes = kSmemUsed + 1024;          // + alignment slack
 };
 
@@ -72,7 +75,30 @@ struct EpiParams {
   TailParams tail;
   int vec;        // 1: every row-wise operand is 32-byte aligned with a 32-byte multiple pitch -> 256-bit accesses
   int has_init;   // row_bias / residual(s) present
+  int w_static;   // W is a parameter: its first tiles are requested before the dependency wait
+  unsigned long long* trace;   // tc_debug_trace: 16 uint64 per CTA, or null
 };
+
+// tc_debug_trace state (host): the buffer and the next free record
+unsigned long long* g_trace_buf = nullptr;
+long long g_trace_cap = 0, g_trace_next = 0;
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+// compiled in only with -DTC_TRACE_BUILD (TC_TRACE_BUILD=1 python -m transcar_b200.build --force): the shipped kernels carry no marks
+#ifdef TC_TRACE_BUILD
+#define TC_TRACE(slot) do { if (trc) trc[slot] = (unsigned long long)clock64(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
 
 // ---- row-per-thread global access: 32 consecutive floats of one row ---------------------------------
 __device__ __forceinline__ void ld256(const float* p, float* v) {
@@ -165,6 +191,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int num_kb = (p.K + BK - 1) / BK;      // a partial last K block is zero-filled by TMA (both operands)
+#ifdef TC_TRACE_BUILD
+  unsigned long long* trc = p.trace ? p.trace + 16ull * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (trc && threadIdx.x == 0) { trc[0] = gtime(); trc[10] = smid(); TC_TRACE(1); }
+#endif
   pdl_trigger();
 
   if (threadIdx.x == 0) {
@@ -179,7 +209,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Static weights (w_static): the W halves of the first ring stages are requested BEFORE the dependency wait - this CTA
+  // is often resident while its predecessor kernel is still draining, and the weight tiles then arrive during that tail
+  // instead of after it.  The stage's expect_tx covers both operands; the A tiles follow after the wait.
+  const int num_pre = p.w_static ? min(num_kb, kStages) : 0;
+  if (threadIdx.x == 0) TC_TRACE(2);
+  if (threadIdx.x == 0) {
+    for (int kb = 0; kb < num_pre; ++kb) {
+      const uint32_t w_dst = smem_base + kb * kStageBytes + (kSplit ? 2 * kABytes : kABytes);
+      mbar_expect_tx(full0 + 8 * kb, kStageBytes);
+      tma_load_2d(w_dst, &map_w, kb * BK, n0, full0 + 8 * kb);
+      if (kSplit) tma_load_2d(w_dst + kBBytes, &map_w, p.K + kb * BK, n0, full0 + 8 * kb);
+    }
+  }
   pdl_wait();            // everything above touched parameters only; activations are read from here on
+  if (threadIdx.x == 0) TC_TRACE(3);
   if (kLN && warp < 2) cluster_arrive();   // these warps own no statistics slots: their share of the cluster barrier
 
   if (warp == 0) {
@@ -188,17 +232,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        mbar_expect_tx(full0 + 8 * s, kStageBytes);
+        const bool w_done = kb < num_pre;            // this stage's W tiles are already in flight (requested before the wait)
+        if (!w_done) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, kStageBytes);
+        }
         const uint32_t a_dst = smem_base + s * kStageBytes;
         if (kSplit) {            // stage = A_hi | A_lo | W_hi | W_lo; the lo halves start at column K of the [rows, 2K] matrices
           tma_load_2d(a_dst, &map_a, kb * BK, m0, full0 + 8 * s);
-          tma_load_2d(a_dst + 2 * kABytes, &map_w, kb * BK, n0, full0 + 8 * s);
+          if (!w_done) tma_load_2d(a_dst + 2 * kABytes, &map_w, kb * BK, n0, full0 + 8 * s);
           tma_load_2d(a_dst + kABytes, &map_a, p.K + kb * BK, m0, full0 + 8 * s);
-          tma_load_2d(a_dst + 2 * kABytes + kBBytes, &map_w, p.K + kb * BK, n0, full0 + 8 * s);
+          if (!w_done) tma_load_2d(a_dst + 2 * kABytes + kBBytes, &map_w, p.K + kb * BK, n0, full0 + 8 * s);
         } else {
           tma_load_2d(a_dst, &map_a, kb * BK, m0, full0 + 8 * s);
-          tma_load_2d(a_dst + kABytes, &map_w, kb * BK, n0, full0 + 8 * s);
+          if (!w_done) tma_load_2d(a_dst + kABytes, &map_w, kb * BK, n0, full0 + 8 * s);
         }
       }
     }
@@ -214,6 +261,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
+        if (kb == 0) TC_TRACE(4);
+        if (kb == num_kb - 1) TC_TRACE(5);
         const uint32_t a_addr = smem_base + s * kStageBytes;
         if (kSplit) {                              // hi*hi, then the two cross terms, into the same accumulator
           const uint64_t dah = make_desc_sw128(a_addr), dal = make_desc_sw128(a_addr + kABytes);
@@ -237,88 +286,94 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4, one accumulator row per thread =====
-    const int quad = warp & 3;
+    // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4: one accumulator row x 32
+    // columns per thread.  (Four warps x 64 columns spent ~1000 cycles per 32-column chunk - ~220 dependent-issue-bound
+    // instructions at ~4.5 cycles each with one or two warps per scheduler, tools/linear_trace.py; eight warps halve it.)
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = m < p.M;
-    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * HN);
     const bool vec = p.vec != 0;
-    const int ncols = min(BN, p.N - n0);
+    const int c0 = half * HN;                                  // this thread's first column inside the tile
+    const int nc = min(BN, p.N - n0) - c0;                     // its valid columns (<= 0: none)
+    const int n = n0 + c0;
     const bool gate = (p.row_gate && row_ok) ? (p.row_gate[m] != 0) : true;
-    if (kLN) {                                                 // statistics slots of this row: empty
-      for (int r = 0; r < kMaxCluster; ++r) reinterpret_cast<unsigned long long*>(s_part)[r * BM + row] = kStatSentinel;
+    if (kLN) {                                                 // statistics slots of this row: empty (each half clears its share)
+      for (int r = half; r < kSlots; r += 2) reinterpret_cast<unsigned long long*>(s_part)[r * BM + row] = kStatSentinel;
       cluster_arrive();                                        // (warps 0 / 1 arrive before their roles start)
     }
     {                                                          // column vectors of this tile (zero beyond N)
       const int j = threadIdx.x - 64;
       if (j < BN) {
-        const int n = n0 + j;
-        s_bias[j] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
-        s_gamma[j] = (kLN && n < p.N) ? p.ln_gamma[n] : 0.f;
-        s_beta[j] = (kLN && n < p.N) ? p.ln_beta[n] : 0.f;
+        const int nn = n0 + j;
+        s_bias[j] = (p.bias && nn < p.N) ? p.bias[nn] : 0.f;
+        s_gamma[j] = (kLN && nn < p.N) ? p.ln_gamma[nn] : 0.f;
+        s_beta[j] = (kLN && nn < p.N) ? p.ln_beta[nn] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps only
     }
 
-    // Input-side terms (bias, per-query row bias, residuals) do not depend on the product.  Fast path (full tile, 32-byte
-    // aligned rows): they are requested right here, while the operands are in flight and the MMAs run, stay in registers
-    // (64 per thread) and are added to the accumulator afterwards.  (Folding them into the accumulator BEFORE the MMAs -
-    // the first version - made the MMAs wait for these loads: measured 4400 cycles for one fp32 residual tile vs 2100 for
-    // operands + MMAs, clock64.)  Partial tiles / unaligned rows fetch them after the accumulator is complete.
-    const bool side_regs = p.has_init && vec && ncols == BN;
-    float side[BN];
+    // Input-side terms (bias, per-query row bias, residuals) do not depend on the product.  Fast path (all 32 columns valid,
+    // 32-byte aligned rows): they are requested right here, while the operands are in flight and the MMAs run, stay in
+    // registers (32 per thread) and are added to the accumulator afterwards.  (Folding them into the accumulator BEFORE the
+    // MMAs - the first version - made the MMAs wait for these loads: measured 4400 cycles for one fp32 residual tile vs 2100
+    // for operands + MMAs, clock64.)  Partial tiles / unaligned rows fetch them after the accumulator is complete.
+    const bool side_regs = p.has_init && vec && nc >= HN;
+    float side[HN];
 #pragma unroll
-    for (int j = 0; j < BN; ++j) side[j] = 0.f;
+    for (int j = 0; j < HN; ++j) side[j] = 0.f;
     if (side_regs && row_ok) {
-      auto add64 = [&](const float* src) {
-        float t[BN];
+      auto add_side = [&](const float* src) {
+        float t[HN];
 #pragma unroll
-        for (int i = 0; i < BN / 8; ++i) ld256(src + 8 * i, t + 8 * i);
+        for (int i = 0; i < HN / 8; ++i) ld256(src + 8 * i, t + 8 * i);
 #pragma unroll
-        for (int j = 0; j < BN; ++j) side[j] += t[j];
+        for (int j = 0; j < HN; ++j) side[j] += t[j];
       };
       if (gate) {
         if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < BN; ++j) side[j] = s_bias[j];
+          for (int j = 0; j < HN; ++j) side[j] = s_bias[c0 + j];
         }
-        if (p.row_bias) add64(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n0);
+        if (p.row_bias) add_side(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n);
       }
-      if (p.residual) add64(p.residual + (long long)m * p.ld_residual + n0);
-      if (p.residual2) add64(p.residual2 + (long long)m * p.ld_residual2 + n0);
+      if (p.residual) add_side(p.residual + (long long)m * p.ld_residual + n);
+      if (p.residual2) add_side(p.residual2 + (long long)m * p.ld_residual2 + n);
     }
 
+    if (threadIdx.x == 64) TC_TRACE(11);
     mbar_wait(accbar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) TC_TRACE(6);
 
-    // pre-activation row chunk:  (gate ? acc + bias + row_bias : 0) + residual + residual2
-    auto load_chunk = [&](int c, float (&v)[32]) {       // c must be a compile-time constant (side[] lives in registers)
-      uint32_t r[32];
-      tmem_ld32(trow + c * 32, r);
-      if (side_regs) {                                   // gated-off rows: side[] holds the residuals only
+    // pre-activation values of this thread:  (gate ? acc + bias + row_bias : 0) + residual + residual2
+    float v[HN];
+    {
+      uint32_t r[HN];
+      tmem_ld32(tcol, r);
+      if (threadIdx.x == 64) TC_TRACE(12);
+      if (side_regs) {                                     // gated-off rows: side[] holds the residuals only
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (gate ? __uint_as_float(r[j]) : 0.f) + side[c * 32 + j];
-        return;
+        for (int j = 0; j < HN; ++j) v[j] = (gate ? __uint_as_float(r[j]) : 0.f) + side[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < HN; ++j) v[j] = gate ? __uint_as_float(r[j]) : 0.f;
+        if (gate && p.bias) {
+#pragma unroll
+          for (int j = 0; j < HN; ++j) v[j] += s_bias[c0 + j];
+        }
+        if (p.has_init && row_ok && nc > 0) {
+          if (gate && p.row_bias) add_row32(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n, nc, vec, v);
+          if (p.residual) add_row32(p.residual + (long long)m * p.ld_residual + n, nc, vec, v);
+          if (p.residual2) add_row32(p.residual2 + (long long)m * p.ld_residual2 + n, nc, vec, v);
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gate ? __uint_as_float(r[j]) : 0.f;
-      if (gate && p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += s_bias[c * 32 + j];
-      }
-      if (!p.has_init || !row_ok) return;
-      const int nc = ncols - c * 32;
-      if (gate && p.row_bias) add_row32(p.row_bias + (long long)(m % p.row_bias_period) * p.ld_row_bias + n0 + c * 32, nc, vec, v);
-      if (p.residual) add_row32(p.residual + (long long)m * p.ld_residual + n0 + c * 32, nc, vec, v);
-      if (p.residual2) add_row32(p.residual2 + (long long)m * p.ld_residual2 + n0 + c * 32, nc, vec, v);
-    };
-    auto store_chunk = [&](int c, float (&v)[32]) {
-      const int nc = ncols - c * 32;
+    }
+    auto store_row = [&](float (&v)[HN]) {
       if (!row_ok || nc <= 0) return;
-      const int n = n0 + c * 32;
       if (p.post_add) add_row32(p.post_add + (long long)m * p.ld_post_add + n, nc, vec, v);
-      if (vec && nc >= 32) {
+      if (vec && nc >= HN) {
         if (p.out_f32) {
           float* dst = p.out_f32 + (long long)m * p.ld_out_f32 + n;
 #pragma unroll
@@ -359,7 +414,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         if (p.out_bf16) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < HN; ++j) {
             if (j < nc) {
               __nv_bfloat16* d16 = p.out_bf16 + (long long)m * p.ld_out_bf16 + n + j;
               if (p.out16 == TC_F16) {
@@ -376,65 +431,59 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     };
 
     if (!kLN) {
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        if (c * 32 >= ncols) break;
-        float v[32];
-        load_chunk(c, v);
+      if (nc > 0) {
         if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < HN; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (kTail && c == 0 && row_ok && n0 == 0) apply_tail(p.tail, m, v);
-        store_chunk(c, v);
+        if (kTail && half == 0 && row_ok && n0 == 0) apply_tail(p.tail, m, v);
+        store_row(v);
       }
     } else {
-      // LayerNorm over the full row: this CTA holds 64 of its N columns, the cluster holds all of them
-      float pre[BN];                   // the pre-LayerNorm row stays in registers: the accumulator is read once
-      float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};   // four partial sums: 16-deep dependent chains, not 64
+      // LayerNorm over the full row: this thread holds 32 of its N columns, its CTA 64, the cluster all of them.  Every
+      // (CTA, half) pair is one contributor: 2 * cluster size partial sums per row, exchanged through shared memory.
+      float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};   // four partial sums: 8-deep dependent chains, not 32
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        load_chunk(c, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { pre[c * 32 + j] = v[j]; p1[j & 3] += v[j]; p2[j & 3] = fmaf(v[j], v[j], p2[j & 3]); }
-      }
+      for (int j = 0; j < HN; ++j) { p1[j & 3] += v[j]; p2[j & 3] = fmaf(v[j], v[j], p2[j & 3]); }
       float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
-      const uint32_t me = cluster_ctarank(), nct = cluster_nctarank();
+      const uint32_t nct = cluster_nctarank();
+      const uint32_t me = 2 * cluster_ctarank() + (uint32_t)half, nslot = 2 * nct;
+      if (threadIdx.x == 64) TC_TRACE(13);
       cluster_wait();                                            // every peer has written its sentinels (long ago)
-      if (nct > 1) {
+      {
         const unsigned long long mine = ((unsigned long long)__float_as_uint(s2) << 32) | __float_as_uint(s1);
         const uint32_t slot = smem_u32(&s_part[me * BM + row]);
-        for (uint32_t r = 1; r < nct; ++r) st_dsmem_u64(slot, (me + r) % nct, mine);
-        float t1 = 0.f, t2 = 0.f;                                // summed in rank order: identical statistics in every CTA
-        for (uint32_t r = 0; r < nct; ++r) {
+        for (uint32_t r = 0; r < nct; ++r) st_dsmem_u64(slot, r, mine);     // into every CTA of the cluster, this one included
+        float t1 = 0.f, t2 = 0.f;                                // summed in slot order: identical statistics in every thread
+        for (uint32_t r = 0; r < nslot; ++r) {
           float o1 = s1, o2 = s2;
           if (r != me) {
             const uint32_t addr = smem_u32(&s_part[r * BM + row]);
-            unsigned long long v = ld_smem_u64(addr);
-            for (uint32_t spins = 0; v == kStatSentinel && spins < kSpinLimit; ++spins) v = ld_smem_u64(addr);
-            o1 = __uint_as_float((uint32_t)v); o2 = __uint_as_float((uint32_t)(v >> 32));
+            unsigned long long w = ld_smem_u64(addr);
+            for (uint32_t spins = 0; w == kStatSentinel && spins < kSpinLimit; ++spins) w = ld_smem_u64(addr);
+            o1 = __uint_as_float((uint32_t)w); o2 = __uint_as_float((uint32_t)(w >> 32));
           }
           t1 += o1; t2 += o2;
         }
         s1 = t1; s2 = t2;
       }
+      if (threadIdx.x == 64) TC_TRACE(14);
       const float inv_n = 1.0f / (float)p.N;
       const float mean = s1 * inv_n;
       const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);    // biased variance, like nn.LayerNorm
       const float rstd = rsqrtf(var + p.ln_eps);
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = fmaf((pre[c * 32 + j] - mean) * rstd, s_gamma[c * 32 + j], s_beta[c * 32 + j]);
-          if (p.relu) v[j] = fmaxf(v[j], 0.f);
-        }
-        store_chunk(c, v);
+      for (int j = 0; j < HN; ++j) {
+        v[j] = fmaf((v[j] - mean) * rstd, s_gamma[c0 + j], s_beta[c0 + j]);
+        if (p.relu) v[j] = fmaxf(v[j], 0.f);
       }
+      store_row(v);
     }
     tc_fence_before();
+    if (threadIdx.x == 64) TC_TRACE(7);
+#ifdef TC_TRACE_BUILD
+    if (trc && lane == 0) atomicMax(trc + 15, (unsigned long long)clock64());     // the last epilogue warp to finish
+#endif
   }
   if (kLN && warp < 2) cluster_wait();     // completes the arrive / wait pair of these warps
   // A CTA leaves only after it has received every peer's statistics, i.e. after the last write into its shared memory;
@@ -444,6 +493,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
   }
+#ifdef TC_TRACE_BUILD
+  if (trc && threadIdx.x == 0) { TC_TRACE(8); trc[9] = gtime(); }
+#endif
 }
 
 // ---- host side: tensor maps -------------------------------------------------------------------------
@@ -465,36 +517,37 @@ EncodeTiledFn encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; long long ld; int rows, cols, box_rows;
+  const void* ptr; long long ld; int rows, cols, box_rows, f32;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows;
+    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows && f32 == o.f32;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
-    return h * 1000003u ^ (size_t)k.box_rows;
+    return h * 1000003u ^ (size_t)(k.box_rows * 2 + k.f32);
   }
 };
 
 // bf16 [rows, cols] row-major with row stride ld (elements); box = [BK cols, box_rows rows], 128B swizzle,
 // out-of-bounds rows read as zero.  Descriptors are pure functions of the key, so they are cached.
-bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CUtensorMap* out) {
+// (f32 = true: fp32 elements, box = [32 cols, box_rows] - the 128-byte-wide output tiles of the epilogue.)
+bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CUtensorMap* out, bool f32 = false) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, ld, rows, cols, box_rows};
+  MapKey key{ptr, ld, rows, cols, box_rows, f32 ? 1 : 0};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("tc_linear: cuTensorMapEncodeTiled entry point not available"); return false; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {(cuuint32_t)(f32 ? BK / 2 : BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("tc_linear: cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
@@ -575,6 +628,13 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   ep.tail = make_tail(a);
   ep.vec = epilogue_vectorizable(a) ? 1 : 0;
   ep.has_init = (a->row_bias || a->residual || a->residual2) ? 1 : 0;
+  static const bool no_prefetch = getenv("TC_NO_WPREFETCH") != nullptr;             // A/B measurements
+  ep.w_static = (a->w_static && !no_prefetch) ? 1 : 0;
+  ep.trace = nullptr;
+  if (g_trace_buf) {
+    const long long ctas = (long long)((a->N + BN - 1) / BN) * ((a->M + BM - 1) / BM);
+    if (g_trace_next + ctas <= g_trace_cap) { ep.trace = g_trace_buf + 16 * g_trace_next; g_trace_next += ctas; }
+  }
   if (a->a_dtype == TC_BF16X2) {
     if (a->tail) return launch_tile<false, true, true>(a, ep, s);
     return a->ln_gamma ? launch_tile<true, true>(a, ep, s) : launch_tile<false, true>(a, ep, s);
@@ -584,3 +644,10 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
 }
 
 }  // namespace tc
+
+extern "C" int tc_debug_trace(uint64_t* device_buf, int64_t records) {
+  tc::g_trace_buf = reinterpret_cast<unsigned long long*>(device_buf);
+  tc::g_trace_cap = device_buf ? records : 0;
+  tc::g_trace_next = 0;
+  return TC_OK;
+}

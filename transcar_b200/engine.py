@@ -74,7 +74,10 @@ class FusionDecoderEngine:
         self.w = {}
         for k, v in f32.items():
             if v.dim() == 2 and (k.endswith("weight") or k.endswith("in_proj_weight")) and "embedding" not in k:
-                self.w[k] = self._cast_w(v)
+                self.w[k] = ops.mark_static(self._cast_w(v))
+        # static weights are prefetched by the GEMM kernels BEFORE their dependency wait (tc_linear_args.w_static): the casts
+        # above must have retired before the first such launch
+        torch.cuda.current_stream().synchronize()
         C = self.C
         self.query = self.query_pos = self.init_ref = None
         self.row_bias_qkv, self.row_bias_aw = [], []
@@ -94,9 +97,9 @@ class FusionDecoderEngine:
         # radar K/V projections of the three layers stacked: [3*2C, C]
         names = ("rf_multihead_attn", "rf_multihead_attn2", "rf_multihead_attn3")
         wkv = torch.cat([f32[n + ".in_proj_weight"][C:] for n in names], 0).contiguous()
-        self.radar_wkv = self._cast_w(wkv)
+        self.radar_wkv = ops.mark_static(self._cast_w(wkv))
         self.radar_bkv = torch.cat([f32[n + ".in_proj_bias"][C:] for n in names], 0).contiguous()
-        self.radar_wq = [self._cast_w(f32[n + ".in_proj_weight"][:C].contiguous()) for n in names]
+        self.radar_wq = [ops.mark_static(self._cast_w(f32[n + ".in_proj_weight"][:C].contiguous())) for n in names]
         self.radar_bq = [f32[n + ".in_proj_bias"][:C].contiguous() for n in names]
         torch.cuda.current_stream().synchronize()
 

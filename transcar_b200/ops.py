@@ -19,11 +19,12 @@ _DT = {torch.float32: TC_F32, torch.bfloat16: TC_BF16, torch.float16: TC_F16}
 class SplitBf16:
     """Split-bf16 matrix (``TC_BF16X2``): logical ``[..., cols]`` stored as bf16 ``[..., 2 * cols]`` = ``hi | lo`` with
     ``hi = bf16(x)``, ``lo = bf16(x - hi)``.  The operand format of the bf16x3 tensor-core mode."""
-    __slots__ = ("t",)
+    __slots__ = ("t", "static")
 
     def __init__(self, t):
         assert t.dtype == torch.bfloat16 and t.shape[-1] % 2 == 0
         self.t = t
+        self.static = False          # see mark_static()
 
     @property
     def shape(self):
@@ -169,6 +170,16 @@ def sample_fwd(feats, ref, lidar2img, attn_logits, pc_range, img_w, img_h, out_d
 
 
 # --------------------------------------------------------------------------------------- K3
+def mark_static(w):
+    """Tag a GEMM weight operand as a parameter that no launch on the stream writes (``tc_linear_args.w_static``): the
+    tensor-core Linear then prefetches its first W tiles before it waits for the previous kernel.  Never tag an activation."""
+    if isinstance(w, SplitBf16):
+        w.static = True
+    else:
+        w._tc_static = True
+    return w
+
+
 def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, residual=None, residual2=None,
            ln=None, ln_eps=1e-5, relu=False, post_add=None, out_f32=None, out_bf16=None,
            want_f32=True, want_bf16=False, out16="bf16", tail=None):
@@ -179,6 +190,7 @@ def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, 
     ``dict(kind='box', anchor=[M,ld], xy_col=, z_col=, from_norm=, pc_range=, geom=(r_lo, r_hi) | None)``; its outputs are
     returned in ``tail['ref_out']`` / ``tail['geom_out']``.  Returns (out_f32 or None, 16-bit output or None)."""
     lib = _lib.load()
+    w_static = bool(getattr(W, "static", False) or getattr(W, "_tc_static", False))
     split = isinstance(A, SplitBf16)
     if split != isinstance(W, SplitBf16):
         raise RuntimeError("transcar_b200.linear: split-bf16 operands come in pairs (A and W)")
@@ -218,6 +230,7 @@ def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, 
         a.ln_beta = _need(ln[1], "ln_beta", torch.float32).data_ptr()
         a.ln_eps = float(ln_eps)
     a.relu = 1 if relu else 0
+    a.w_static = 1 if w_static else 0
     if post_add is not None:
         pa, ldpa = _rows(_need(post_add, "post_add", torch.float32), "post_add")
         a.post_add, a.ld_post_add = pa.data_ptr(), ldpa
