@@ -76,6 +76,7 @@ struct EpiParams {
   int vec;        // 1: every row-wise operand is 32-byte aligned with a 32-byte multiple pitch -> 256-bit accesses
   int has_init;   // row_bias / residual(s) present
   int w_static;   // W is a parameter: its first tiles are requested before the dependency wait
+  int tma_out;    // outputs leave through shared-memory staging + TMA tile stores (map_o32 / map_o16) instead of row stores
   unsigned long long* trace;   // tc_debug_trace: 16 uint64 per CTA, or null
 };
 
@@ -172,7 +173,8 @@ __device__ __forceinline__ unsigned long long ld_smem_u64(uint32_t addr) {
 
 template <bool kLN, bool kSplit, bool kTail>
 __global__ void __launch_bounds__(kThreads, 2)
-linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const EpiParams p) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_o16, const EpiParams p) {
   using C = Cfg<kSplit>;
   constexpr int kStages = C::kStages;
   constexpr uint32_t kStageBytes = C::kStageBytes, kOffBars = C::kOffBars, kOffVec = C::kOffVec, kOffPart = C::kOffPart;
@@ -370,9 +372,57 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
+    // Output side.  Fast path (tma_out): every warp stages its 32 rows x 32 columns in shared memory - the operand ring is
+    // free once the accumulator is complete - in the swizzled layout of the output tensor maps (conflict-free 128-bit
+    // st.shared) and one lane issues TMA tile stores: whole 128 / 64-byte row segments per request instead of 32-byte
+    // sectors of 32 different lines per st.global (the row stores held the epilogue at ~1 sector per clock and SM:
+    // tools/linear_trace.py, 3700 of a CTA's 10400 cycles).  Rows beyond M / columns beyond N are clipped by the TMA unit.
     auto store_row = [&](float (&v)[HN]) {
-      if (!row_ok || nc <= 0) return;
-      if (p.post_add) add_row32(p.post_add + (long long)m * p.ld_post_add + n, nc, vec, v);
+      if (nc <= 0) return;
+      if (p.post_add && row_ok) add_row32(p.post_add + (long long)m * p.ld_post_add + n, nc, vec, v);
+      if (p.tma_out) {
+        const uint32_t stg = smem_base + (uint32_t)(warp - 2) * 8192u;      // f32 tile 4 KB | 16-bit (hi) 2 KB | lo 2 KB
+        if (p.out_f32) {
+          const uint32_t rowa = stg + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            sts128(rowa + (uint32_t)((c ^ (lane & 7)) << 4), __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                   __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+        }
+        if (p.out_bf16) {
+          uint32_t u[16];
+          if (p.out16 == TC_F16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = pack_f16_sat(v[2 * i], v[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+          }
+          const uint32_t rowa = stg + 4096u + (uint32_t)lane * 64u;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sts128(rowa + (uint32_t)((c ^ sw) << 4), u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
+          if (p.out16 == TC_BF16X2) {            // lo = bf16(v - hi) at column N + n
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = pack_bf16(v[2 * i] - bf16_lo(u[i]), v[2 * i + 1] - bf16_hi(u[i]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sts128(rowa + 2048u + (uint32_t)((c ^ sw) << 4), u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int mrow = m0 + quad * 32;
+        if (lane == 0 && mrow < p.M) {
+          if (p.out_f32) tma_store_2d(&map_o32, stg, n, mrow);
+          if (p.out_bf16) {
+            tma_store_2d(&map_o16, stg + 4096u, n, mrow);
+            if (p.out16 == TC_BF16X2) tma_store_2d(&map_o16, stg + 6144u, p.N + n, mrow);
+          }
+          tma_store_commit();
+        }
+        return;
+      }
+      if (!row_ok) return;
       if (vec && nc >= HN) {
         if (p.out_f32) {
           float* dst = p.out_f32 + (long long)m * p.ld_out_f32 + n;
@@ -479,6 +529,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       store_row(v);
     }
+    if (p.tma_out && lane == 0) tma_store_wait_read();     // the staging tiles live in this CTA's shared memory
     tc_fence_before();
     if (threadIdx.x == 64) TC_TRACE(7);
 #ifdef TC_TRACE_BUILD
@@ -516,39 +567,45 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// kinds of tensor map: the bf16 operand tiles, and the two output tiles of the TMA-store epilogue
+enum MapKind { kMapOperand = 0, kMapOutF32 = 1, kMapOut16 = 2 };
 struct MapKey {
-  const void* ptr; long long ld; int rows, cols, box_rows, f32;
+  const void* ptr; long long ld; int rows, cols, box_rows, kind;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows && f32 == o.f32;
+    return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows && kind == o.kind;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
-    return h * 1000003u ^ (size_t)(k.box_rows * 2 + k.f32);
+    return h * 1000003u ^ (size_t)(k.box_rows * 4 + k.kind);
   }
 };
 
-// bf16 [rows, cols] row-major with row stride ld (elements); box = [BK cols, box_rows rows], 128B swizzle,
-// out-of-bounds rows read as zero.  Descriptors are pure functions of the key, so they are cached.
-// (f32 = true: fp32 elements, box = [32 cols, box_rows] - the 128-byte-wide output tiles of the epilogue.)
-bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CUtensorMap* out, bool f32 = false) {
+// [rows, cols] row-major with row stride ld (elements), out-of-bounds rows / columns read as zero and are not written.
+//   kMapOperand  bf16, box = [BK cols, box_rows rows], 128B swizzle (one swizzle row per K block row)
+//   kMapOutF32   fp32, box = [32 cols, box_rows] = 128-byte rows, 128B swizzle      } the per-warp staging tiles of the
+//   kMapOut16    16-bit, box = [32 cols, box_rows] = 64-byte rows, 64B swizzle      } epilogue (bf16 and fp16 alike)
+// Descriptors are pure functions of the key, so they are cached.
+bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CUtensorMap* out, MapKind kind = kMapOperand) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, ld, rows, cols, box_rows, f32 ? 1 : 0};
+  MapKey key{ptr, ld, rows, cols, box_rows, (int)kind};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("tc_linear: cuTensorMapEncodeTiled entry point not available"); return false; }
+  const bool f32 = kind == kMapOutF32;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
-  cuuint32_t box[2] = {(cuuint32_t)(f32 ? BK / 2 : BK), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(kind == kMapOperand ? BK : 32), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = fn(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, kind == kMapOut16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  kind == kMapOperand ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("tc_linear: cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
   if (cache.size() > 4096) cache.clear();
@@ -564,6 +621,12 @@ int launch_tile(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
   constexpr size_t kSmemBytes = Cfg<kSplit>::kSmemBytes;
   if (!get_map(a->A, a->lda, a->M, kcols, BM, &ma)) return TC_ERR_SHAPE;
   if (!get_map(a->W, a->ldw, a->N, kcols, BN, &mw)) return TC_ERR_SHAPE;
+  CUtensorMap mo32 = ma, mo16 = ma;                  // placeholders when an output (or the TMA-store path) is absent
+  if (ep.tma_out) {
+    if (a->out_f32 && !get_map(a->out_f32, a->ld_out_f32, a->M, a->N, 32, &mo32, kMapOutF32)) return TC_ERR_SHAPE;
+    const int cols16 = ep.out16 == TC_BF16X2 ? 2 * a->N : a->N;
+    if (a->out_bf16 && !get_map(a->out_bf16, a->ld_out_bf16, a->M, cols16, 32, &mo16, kMapOut16)) return TC_ERR_SHAPE;
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<kLN, kSplit, kTail>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
@@ -573,7 +636,7 @@ int launch_tile(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
   const unsigned ntiles = (unsigned)((a->N + BN - 1) / BN);
   // LayerNorm: the CTAs of one row block form a cluster and exchange row statistics
   cudaError_t e = launch(linear_tc_kernel<kLN, kSplit, kTail>, dim3(ntiles, (unsigned)((a->M + BM - 1) / BM)), dim3(kThreads), kSmemBytes, s,
-                         kLN ? ntiles : 1u, ma, mw, ep);
+                         kLN ? ntiles : 1u, ma, mw, mo32, mo16, ep);
   if (e != cudaSuccess) { set_error("tc_linear(tcgen05): %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return (int)e; }
   count_launch();
   return check_launch("tc_linear(tcgen05)");
@@ -630,6 +693,12 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   ep.has_init = (a->row_bias || a->residual || a->residual2) ? 1 : 0;
   static const bool no_prefetch = getenv("TC_NO_WPREFETCH") != nullptr;             // A/B measurements
   ep.w_static = (a->w_static && !no_prefetch) ? 1 : 0;
+  // TMA-store epilogue: 16-byte aligned bases and row pitches; a split output needs whole 32-column tiles (a partial hi
+  // tile would reach into the lo half)
+  static const bool no_tma_store = getenv("TC_NO_TMA_STORE") != nullptr;             // A/B measurements
+  ep.tma_out = !no_tma_store && (a->out_f32 || a->out_bf16) && a->N >= 64 &&     // (narrow outputs: the row stores are as fast)
+               (!a->out_f32 || (al16(a->out_f32) && (a->ld_out_f32 * 4) % 16 == 0)) &&
+               (!a->out_bf16 || (al16(a->out_bf16) && (a->ld_out_bf16 * 2) % 16 == 0 && (ep.out16 != TC_BF16X2 || a->N % 32 == 0)));
   ep.trace = nullptr;
   if (g_trace_buf) {
     const long long ctas = (long long)((a->N + BN - 1) / BN) * ((a->M + BM - 1) / BM);
