@@ -34,7 +34,7 @@ extern "C" {
 #define TC_API
 #endif
 
-#define TC_ABI_VERSION 6
+#define TC_ABI_VERSION 7
 #define TC_MAX_LEVELS 4
 #define TC_MAX_CAMS 8
 
@@ -179,6 +179,27 @@ typedef struct {
   int32_t w_static;                               /* W is a parameter no earlier launch of the stream writes (see above) */
 } tc_linear_args;
 TC_API int tc_linear(const tc_linear_args* a, tc_stream_t stream);
+
+/* Fused feed-forward block in the bf16x3 operand format:  Y = LayerNorm(residual + W2 relu(W1 X + b1) + b2).
+ * Replaces the mmcv FFN + norm of a decoder layer (BaseTransformerLayer 'ffn', 'norm': ffns.0.layers.0.0 / layers.1 +
+ * norms.2, configured at projects/configs/detr3d/detr3d_res101_gridmask.py:76-84) and H:583-586 (rf_linear2(relu(
+ * rf_linear1(x))) + rf_norm3) - the same result as two tc_linear calls (relu, then residual + LayerNorm), as one launch
+ * in which the [M, H] hidden activation never leaves the SM pair that produced it (csrc/ffn_tc.cu).
+ * X [M, 2C], W1 [H, 2C], W2 [C, 2H] are split bf16 (TC_BF16X2: hi | lo), residual fp32 [M, C] (the identity branch, normally
+ * X in fp32).  Outputs: out_f32 [M, C] and / or out16 split bf16 [M, 2C]; either may be NULL.  Built for C = 256, H = 512 (the
+ * TransCAR configs); other sizes return TC_ERR_SHAPE and callers fall back to two tc_linear calls.  w_static: as in tc_linear. */
+typedef struct {
+  const void* X; int64_t ldx;
+  const void* W1; int64_t ldw1; const float* b1;
+  const void* W2; int64_t ldw2; const float* b2;
+  const float* residual; int64_t ld_residual;
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
+  float* out_f32; int64_t ld_out_f32;
+  void* out16; int64_t ld_out16;
+  int32_t M, C, H;
+  int32_t w_static;
+} tc_ffn_args;
+TC_API int tc_ffn(const tc_ffn_args* a, tc_stream_t stream);
 
 /* Fused 3 -> C position encoder head: Y = ReLU(LayerNorm(Linear_{3->C}(f(x)))), f = inverse_sigmoid (eps 1e-5,
  * T:17-32) when logit_input != 0 else identity.  Replaces T:377 (position_encoder[0:3]) and H:533

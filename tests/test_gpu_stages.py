@@ -254,6 +254,50 @@ def test_linear_matches_oracle_ffn_block(ops):
     torch.testing.assert_close(y, want, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("M", [7200, 640, 100])
+def test_ffn_fused_matches_oracle_and_unfused(ops, M):
+    """tc_ffn (one launch: both GEMMs of the feed-forward block, residual, LayerNorm) vs the oracle's FFN + norm in fp32
+    and vs the two-launch bf16x3 path it replaces (mmcv FFN + norms.2; H:583-586).  M = 7200 is the benched size (57 row
+    blocks, the last with 32 valid rows), 100 a single partial block."""
+    sd = {k: v.to(dev()) for k, v in synthetic.make_state_dict(1, 128).items()}
+    p = "transformer.decoder.layers.2"
+    x = rnd((M, 256), 21 + M)
+    x[3] *= 30.0                          # a row with a large dynamic range
+    W1, W2 = ops.mark_static(ops.cast_split(sd[p + ".ffns.0.layers.0.0.weight"])), ops.mark_static(ops.cast_split(sd[p + ".ffns.0.layers.1.weight"]))
+    b1, b2 = sd[p + ".ffns.0.layers.0.0.bias"], sd[p + ".ffns.0.layers.1.bias"]
+    ln = (sd[p + ".norms.2.weight"], sd[p + ".norms.2.bias"])
+    x16 = ops.cast_split(x)
+    assert ops.ffn_supported(x16, W1, W2)
+    y32, y16 = ops.ffn(x16, W1, b1, W2, b2, x, ln)
+    torch.cuda.synchronize()
+    hh = F.relu(O.lin(sd, p + ".ffns.0.layers.0.0", x))
+    want = O.lnorm(sd, p + ".norms.2", x + O.lin(sd, p + ".ffns.0.layers.1", hh))
+    torch.testing.assert_close(y32, want, rtol=2e-5, atol=2e-5)
+    # the split 16-bit copy carries the same values to ~16 mantissa bits
+    hi, lo = y16.t[:, :256].float(), y16.t[:, 256:].float()
+    torch.testing.assert_close(hi + lo, y32, rtol=2e-5, atol=1e-6)
+    assert torch.equal(hi, y32.bfloat16().float())
+    # the two launches it replaces
+    h, h16 = ops.linear(x16, W1, b1, relu=True, want_f32=False, want_bf16=True, out16="split")
+    u32, _ = ops.linear(h16, W2, b2, residual=x, ln=ln, want_bf16=True, out16="split")
+    torch.testing.assert_close(y32, u32, rtol=1e-5, atol=1e-5)
+    # outputs are optional one by one
+    only32, none16 = ops.ffn(x16, W1, b1, W2, b2, x, ln, want_16=False)
+    none32, only16 = ops.ffn(x16, W1, b1, W2, b2, x, ln, want_f32=False)
+    assert none16 is None and none32 is None
+    assert torch.equal(only32, y32) and torch.equal(only16.t, y16.t)
+
+
+def test_ffn_bad_arguments(ops):
+    x = ops.cast_split(rnd((64, 256), 1))
+    W1, W2 = ops.cast_split(rnd((512, 256), 2)), ops.cast_split(rnd((256, 512), 3))
+    b1, b2, g = rnd((512,), 4), rnd((256,), 5), rnd((256,), 6)
+    with pytest.raises(RuntimeError, match="C = 256, H = 512"):
+        ops.ffn(x, ops.cast_split(rnd((256, 256), 7)), b1, W2, b2, rnd((64, 256), 8), (g, g))
+    with pytest.raises(RuntimeError, match="residual has shape"):
+        ops.ffn(x, W1, b1, W2, b2, rnd((64, 128), 8), (g, g))
+
+
 def test_linear_bad_arguments(ops):
     A, W = rnd((4, 8), 1), rnd((3, 8), 2)
     with pytest.raises(RuntimeError, match="CUDA tensor"):

@@ -29,6 +29,7 @@
 #include <cuda_fp16.h>
 
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 #include "tc_sm100.cuh"
 
 namespace tc {
@@ -79,97 +80,6 @@ struct EpiParams {
   int tma_out;    // outputs leave through shared-memory staging + TMA tile stores (map_o32 / map_o16) instead of row stores
   unsigned long long* trace;   // tc_debug_trace: 16 uint64 per CTA, or null
 };
-
-// tc_debug_trace state (host): the buffer and the next free record
-unsigned long long* g_trace_buf = nullptr;
-long long g_trace_cap = 0, g_trace_next = 0;
-
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ unsigned smid() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
-  return r;
-}
-// compiled in only with -DTC_TRACE_BUILD (TC_TRACE_BUILD=1 python -m transcar_b200.build --force): the shipped kernels carry no marks
-#ifdef TC_TRACE_BUILD
-#define TC_TRACE(slot) do { if (trc) trc[slot] = (unsigned long long)clock64(); } while (0)
-#else
-#define TC_TRACE(slot) do { } while (0)
-#endif
-
-// ---- row-per-thread global access: 32 consecutive floats of one row ---------------------------------
-__device__ __forceinline__ void ld256(const float* p, float* v) {
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void st256(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void st256u(void* p, const uint32_t* v) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-// v[j] += row[j], j < 32 (ncols valid columns); 256-bit loads for every complete group of 8 columns
-__device__ __forceinline__ void add_row32(const float* row, int ncols, bool vec, float (&v)[32]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (vec && 8 * i + 8 <= ncols) {
-      float t[8];
-      ld256(row + 8 * i, t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[8 * i + j] += t[j];
-    } else {
-#pragma unroll
-      for (int j = 8 * i; j < 8 * i + 8; ++j)
-        if (j < ncols) v[j] += row[j];
-    }
-  }
-}
-
-__device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {       // saturating: +-65504 instead of inf
-  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-  __half2 v = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-// LayerNorm statistics exchange between the CTAs of a cluster: every CTA PUSHES its per-row (sum, sum of squares) into
-// slot [own rank][row] of each peer's shared memory (one relaxed 64-bit store: the value is its own flag, nothing else is
-// published with it) and polls its own slots, which start as a NaN sentinel.  No cluster barrier sits on the critical path (the first version spent 41 % of its warp samples in
-// barrier.cluster arrive / wait - ncu, profiles/r01_ncu_linear.txt): the only one (sentinels written before any peer
-// may push) is split, arrive right after the init, wait just before the first push, ~5 us later.
-// a NaN pair with a payload no arithmetic produces (sums of NaN inputs are the canonical 0x7fffffff): never a real value
-constexpr unsigned long long kStatSentinel = 0xffc0dead'ffc0deadull;
-__device__ __forceinline__ void st_dsmem_u64(uint32_t local_addr, uint32_t rank, unsigned long long v) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_smem_u64(uint32_t addr) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-  return v;
-}
 
 template <bool kLN, bool kSplit, bool kTail>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -567,8 +477,6 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// kinds of tensor map: the bf16 operand tiles, and the two output tiles of the TMA-store epilogue
-enum MapKind { kMapOperand = 0, kMapOutF32 = 1, kMapOut16 = 2 };
 struct MapKey {
   const void* ptr; long long ld; int rows, cols, box_rows, kind;
   bool operator==(const MapKey& o) const {
@@ -583,12 +491,10 @@ struct MapKeyHash {
   }
 };
 
-// [rows, cols] row-major with row stride ld (elements), out-of-bounds rows / columns read as zero and are not written.
-//   kMapOperand  bf16, box = [BK cols, box_rows rows], 128B swizzle (one swizzle row per K block row)
-//   kMapOutF32   fp32, box = [32 cols, box_rows] = 128-byte rows, 128B swizzle      } the per-warp staging tiles of the
-//   kMapOut16    16-bit, box = [32 cols, box_rows] = 64-byte rows, 64B swizzle      } epilogue (bf16 and fp16 alike)
-// Descriptors are pure functions of the key, so they are cached.
-bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CUtensorMap* out, MapKind kind = kMapOperand) {
+}  // namespace
+
+// see tc_epilogue.cuh
+bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CUtensorMap* out, MapKind kind) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{ptr, ld, rows, cols, box_rows, (int)kind};
@@ -613,6 +519,8 @@ bool get_map(const void* ptr, long long ld, int rows, int cols, int box_rows, CU
   *out = m;
   return true;
 }
+
+namespace {
 
 template <bool kLN, bool kSplit, bool kTail = false>
 int launch_tile(const tc_linear_args* a, const EpiParams& ep, cudaStream_t s) {
@@ -699,11 +607,7 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   ep.tma_out = !no_tma_store && (a->out_f32 || a->out_bf16) && a->N >= 64 &&     // (narrow outputs: the row stores are as fast)
                (!a->out_f32 || (al16(a->out_f32) && (a->ld_out_f32 * 4) % 16 == 0)) &&
                (!a->out_bf16 || (al16(a->out_bf16) && (a->ld_out_bf16 * 2) % 16 == 0 && (ep.out16 != TC_BF16X2 || a->N % 32 == 0)));
-  ep.trace = nullptr;
-  if (g_trace_buf) {
-    const long long ctas = (long long)((a->N + BN - 1) / BN) * ((a->M + BM - 1) / BM);
-    if (g_trace_next + ctas <= g_trace_cap) { ep.trace = g_trace_buf + 16 * g_trace_next; g_trace_next += ctas; }
-  }
+  ep.trace = trace_take((long long)((a->N + BN - 1) / BN) * ((a->M + BM - 1) / BM));
   if (a->a_dtype == TC_BF16X2) {
     if (a->tail) return launch_tile<false, true, true>(a, ep, s);
     return a->ln_gamma ? launch_tile<true, true>(a, ep, s) : launch_tile<false, true>(a, ep, s);
@@ -712,6 +616,19 @@ int linear_tc_launch(const tc_linear_args* a, cudaStream_t s) {
   return a->ln_gamma ? launch_tile<true, false>(a, ep, s) : launch_tile<false, false>(a, ep, s);
 }
 
+}  // namespace tc
+
+namespace tc {
+namespace {
+unsigned long long* g_trace_buf = nullptr;         // tc_debug_trace state: the buffer and the next free record
+long long g_trace_cap = 0, g_trace_next = 0;
+}  // namespace
+unsigned long long* trace_take(long long ctas) {
+  if (!g_trace_buf || g_trace_next + ctas > g_trace_cap) return nullptr;
+  unsigned long long* r = g_trace_buf + 16 * g_trace_next;
+  g_trace_next += ctas;
+  return r;
+}
 }  // namespace tc
 
 extern "C" int tc_debug_trace(uint64_t* device_buf, int64_t records) {

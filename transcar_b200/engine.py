@@ -35,6 +35,7 @@ RADIUS_CLAMP = ((1.0, 2.0), (1.0, 2.0), (0.5, 1.0))      # H:567, H:635, H:693
 # sampling kernel then shares SMs with the branch's remaining GEMM (it needs whole SMs: 192 KB rings) and its in-step
 # duration grows from 18.4 to 25.2 us - not worth it.
 _JOIN_FULL = not os.environ.get("TC_JOIN_SPLIT")
+_FUSE_FFN = not os.environ.get("TC_NO_FFN_FUSE")          # A/B: the fused feed-forward launch (tc_ffn) vs two Linear launches
 
 
 class FusionDecoderEngine:
@@ -196,6 +197,15 @@ class FusionDecoderEngine:
     def _ln(self, key):
         return (self.f32[key + ".weight"], self.f32[key + ".bias"])
 
+    def _ffn(self, x32, x16, key1, key2, norm):
+        """x + W2 relu(W1 x) followed by LayerNorm (mmcv FFN + norm; H:583-586): one fused launch in the bf16x3 mode
+        (``tc_ffn``), else two Linear launches."""
+        w1, w2 = self.w[key1 + ".weight"], self.w[key2 + ".weight"]
+        if _FUSE_FFN and self.x3 and ops.ffn_supported(x16, w1, w2):
+            return ops.ffn(x16, w1, self.f32[key1 + ".bias"], w2, self.f32[key2 + ".bias"], x32, self._ln(norm))
+        h = self._lin(x16, key1, feed=True, relu=True)
+        return self._lin(h, key2, both=True, residual=x32, ln=self._ln(norm))
+
     def _prep_feats(self, mlvl_feats):
         """Feature hand-off: channels-last maps are taken zero-copy (bf16 in the tensor-core modes, fp32 in the fp32 and
         bf16x3 modes); NCHW fp32 maps are re-laid out by ``tc_nchw_to_nhwc`` (to bf16 only in the one-pass bf16 mode -
@@ -327,8 +337,7 @@ class FusionDecoderEngine:
             x32, x16 = self._lin(s.view(M, C), p + "attentions.1.output_proj", both=True,
                                  residual=x32, residual2=pos_feat, ln=self._ln(p + "norms.1"))
             # --- FFN (mmcv FFN: x + W2 relu(W1 x)) + norm
-            h = self._lin(x16, p + "ffns.0.layers.0.0", feed=True, relu=True)
-            x32, x16 = self._lin(h, p + "ffns.0.layers.1", both=True, residual=x32, ln=self._ln(p + "norms.2"))
+            x32, x16 = self._ffn(x32, x16, p + "ffns.0.layers.0.0", p + "ffns.0.layers.1", p + "norms.2")
             # --- branch: iterative refinement (T:190-203) and the next layer's position encoder (T:377).  The next
             # layer's self-attention needs only x, so this chain (~45 us) hides behind in_proj + attention + out_proj.
             with self._branch(0):
@@ -460,8 +469,7 @@ class FusionDecoderEngine:
                                          out_dtype="split" if self.x3 else None)
             x32, x16 = self._lin(att.view(M, C), "rf_multihead_attn" + m + ".out_proj", both=True,
                                  row_gate=row_any.view(M), residual=x32, ln=self._ln("rf_norm2" + s))
-            h = self._lin(x16, "rf_linear1" + s, feed=True, relu=True)
-            x32, x16 = self._lin(h, "rf_linear2" + s, both=True, residual=x32, ln=self._ln("rf_norm3" + s))
+            x32, x16 = self._ffn(x32, x16, "rf_linear1" + s, "rf_linear2" + s, "rf_norm3" + s)
             if li + 1 < 3:
                 with self._branch(1):  # next layer's query projection: runs beside this layer's regression head
                     qp_next = q_proj(li + 1, x16)

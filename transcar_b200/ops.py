@@ -280,6 +280,47 @@ def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, 
     return out_f32, ret16
 
 
+def ffn_supported(x, W1, W2):
+    """True when ``tc_ffn`` (the fused feed-forward launch) covers these operands: split bf16, C = 256, H = 512."""
+    return (isinstance(x, SplitBf16) and isinstance(W1, SplitBf16) and isinstance(W2, SplitBf16)
+            and x.shape[-1] == 256 and tuple(W1.shape) == (512, 256) and tuple(W2.shape) == (256, 512))
+
+
+def ffn(x, W1, b1, W2, b2, residual, ln, ln_eps=1e-5, want_f32=True, want_16=True):
+    """LayerNorm(residual + W2 relu(W1 x + b1) + b2) as ONE launch (``tc_ffn``, csrc/ffn_tc.cu).  x [M, C], W1 [H, C],
+    W2 [C, H] are :class:`SplitBf16`; residual fp32 [M, C]; ``ln`` = (gamma, beta).  Returns (fp32 [M, C] or None,
+    SplitBf16 [M, C] or None)."""
+    lib = _lib.load()
+    if not ffn_supported(x, W1, W2):
+        raise RuntimeError("transcar_b200.ffn: needs split-bf16 operands with C = 256, H = 512 (use two linear() calls)")
+    w_static = bool(W1.static and W2.static)
+    X, ldx = _rows(_need(x.t, "x"), "x")
+    w1, ldw1 = _rows(_need(W1.t, "W1"), "W1")
+    w2, ldw2 = _rows(_need(W2.t, "W2"), "W2")
+    M, Cc, H = X.shape[0], X.shape[1] // 2, w1.shape[0]
+    r, ldr = _rows(_need(residual, "residual", torch.float32), "residual")
+    if r.shape != (M, Cc):
+        raise RuntimeError(f"transcar_b200.ffn: residual has shape {tuple(r.shape)}, expected {(M, Cc)}")
+    a = _lib.FfnArgs()
+    a.X, a.ldx, a.W1, a.ldw1, a.W2, a.ldw2 = X.data_ptr(), ldx, w1.data_ptr(), ldw1, w2.data_ptr(), ldw2
+    a.b1 = _need(b1, "b1", torch.float32).data_ptr()
+    a.b2 = _need(b2, "b2", torch.float32).data_ptr()
+    a.residual, a.ld_residual = r.data_ptr(), ldr
+    a.ln_gamma = _need(ln[0], "ln_gamma", torch.float32).data_ptr()
+    a.ln_beta = _need(ln[1], "ln_beta", torch.float32).data_ptr()
+    a.ln_eps = float(ln_eps)
+    a.M, a.C, a.H, a.w_static = M, Cc, H, 1 if w_static else 0
+    o32 = torch.empty((M, Cc), device=X.device, dtype=torch.float32) if want_f32 else None
+    o16 = SplitBf16(torch.empty((M, 2 * Cc), device=X.device, dtype=torch.bfloat16)) if want_16 else None
+    if o32 is not None:
+        a.out_f32, a.ld_out_f32 = o32.data_ptr(), Cc
+    if o16 is not None:
+        a.out16, a.ld_out16 = o16.t.data_ptr(), 2 * Cc
+    label = "ffn" if TIMELINE is None else f"ffn M{M} C{Cc} H{H} bf16x3+res+ln"
+    _lib.check(_call(label, lib.tc_ffn, C.byref(a), _stream()), "ffn")
+    return o32, o16
+
+
 def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, want_f32=True, want_bf16=False,
                 out16="bf16"):
     """ReLU(LN(Linear_{3->C}(f(x[:, :3])))); x [M, ldx>=3] fp32.  ``out16``: 'bf16' or 'split'."""
