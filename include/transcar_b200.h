@@ -34,7 +34,7 @@ extern "C" {
 #define TC_API
 #endif
 
-#define TC_ABI_VERSION 7
+#define TC_ABI_VERSION 8
 #define TC_MAX_LEVELS 4
 #define TC_MAX_CAMS 8
 
@@ -200,6 +200,31 @@ typedef struct {
   int32_t w_static;
 } tc_ffn_args;
 TC_API int tc_ffn(const tc_ffn_args* a, tc_stream_t stream);
+
+/* Fused three-layer head in the bf16x3 operand format:  Y = W3 f2(W2 f1(W1 X + b1) + b2) + b3 with f = ReLU, or
+ * ReLU(LayerNorm(.)) when that layer's ln gamma / beta are given, followed by the row-local tail of tc_linear
+ * (TC_TAIL_REF_UPDATE / TC_TAIL_BOX on the first 8 output columns; same tail_* fields).  Replaces the three tc_linear launches
+ * of reg_branches[l] (Linear-ReLU-Linear-ReLU-Linear, H:141-152; used at T:190-203), final_reg* (H:588-600, H:660-665,
+ * H:718-723) and final_cls* (Linear-LN-ReLU-Linear-LN-ReLU-Linear, H:128-139): the two hidden activations stay in tensor /
+ * shared memory of the CTA that owns the 128 rows (csrc/mlp_tc.cu).  X [M, 2C], W1 / W2 [C, 2C], W3 [N3, 2C] are split bf16;
+ * out_f32 [M, N3] fp32.  Built for C = 256, N3 <= 32; other sizes return TC_ERR_SHAPE (callers use three tc_linear calls). */
+typedef struct {
+  const void* X; int64_t ldx;
+  const void* W1; int64_t ldw1; const float* b1; const float* ln1_gamma; const float* ln1_beta;
+  const void* W2; int64_t ldw2; const float* b2; const float* ln2_gamma; const float* ln2_beta;
+  const void* W3; int64_t ldw3; const float* b3;
+  float ln_eps;
+  float* out_f32; int64_t ld_out_f32;
+  int32_t M, C, N3;
+  int32_t w_static;
+  int32_t tail;
+  const float* tail_in; int64_t ld_tail_in;
+  float* tail_ref_out; float* tail_geom_out;
+  int32_t tail_xy_col, tail_z_col, tail_from_norm;
+  float tail_pc_range[6];
+  float tail_r_lo, tail_r_hi;
+} tc_mlp_args;
+TC_API int tc_mlp(const tc_mlp_args* a, tc_stream_t stream);
 
 /* Fused 3 -> C position encoder head: Y = ReLU(LayerNorm(Linear_{3->C}(f(x)))), f = inverse_sigmoid (eps 1e-5,
  * T:17-32) when logit_input != 0 else identity.  Replaces T:377 (position_encoder[0:3]) and H:533

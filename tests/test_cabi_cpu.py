@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == names, "ctypes binding and header disagree"
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.tc_abi_version() == _lib.ABI_VERSION == 7
+    assert lib.tc_abi_version() == _lib.ABI_VERSION == 8
     assert lib.tc_launch_count() >= 0
 
 

@@ -298,6 +298,73 @@ def test_ffn_bad_arguments(ops):
         ops.ffn(x, W1, b1, W2, b2, rnd((64, 128), 8), (g, g))
 
 
+@pytest.mark.parametrize("M", [7200, 200])
+def test_mlp_fused_heads_match_oracle_and_unfused(ops, M):
+    """tc_mlp (one launch: three Linear layers of a head, hidden activations on chip) vs the oracle in fp32 and vs the three
+    bf16x3 tc_linear launches it replaces, tails included: the refinement branch (reg_branches, T:190-203), a regression
+    head with the box tail (final_reg, H:588-600) and a classification head with its LayerNorms (final_cls, H:128-139)."""
+    sd = {k: v.to(dev()) for k, v in synthetic.make_state_dict(1, 128).items()}
+    x = rnd((M, 256), 77 + M)
+    x16 = ops.cast_split(x)
+    pc = synthetic.PC_RANGE
+    ref = torch.rand((M, 3), generator=torch.Generator().manual_seed(5)).to(dev())
+    W = lambda k: ops.mark_static(ops.cast_split(sd[k + ".weight"]))
+
+    def unfused(keys, lns, tail):
+        a, a16 = ops.linear(x16, W(keys[0]), sd[keys[0] + ".bias"], ln=lns[0], relu=True, want_bf16=True, out16="split")
+        b, b16 = ops.linear(a16, W(keys[1]), sd[keys[1] + ".bias"], ln=lns[1], relu=True, want_bf16=True, out16="split")
+        y, _ = ops.linear(b16, W(keys[2]), sd[keys[2] + ".bias"], tail=tail)
+        return y
+
+    # ---- refinement branch + reference update (+ first radar geometry)
+    keys = tuple(f"reg_branches.3.{i}" for i in (0, 2, 4))
+    t_f = dict(kind="ref_update", ref=ref, pc_range=pc, geom=(1.0, 2.0))
+    y = ops.mlp(x16, W(keys[0]), sd[keys[0] + ".bias"], W(keys[1]), sd[keys[1] + ".bias"], W(keys[2]), sd[keys[2] + ".bias"], tail=t_f)
+    want = O.lin(sd, keys[2], F.relu(O.lin(sd, keys[1], F.relu(O.lin(sd, keys[0], x)))))
+    torch.testing.assert_close(y, want, rtol=2e-5, atol=2e-5)
+    t_u = dict(kind="ref_update", ref=ref, pc_range=pc, geom=(1.0, 2.0))
+    torch.testing.assert_close(y, unfused(keys, (None, None), t_u), rtol=1e-5, atol=1e-5)
+    # the tail is a function of the row's outputs: bit-identical to the stand-alone kernels run on this result
+    assert torch.equal(t_f["ref_out"], ops.ref_update(y, ref))
+    assert torch.equal(t_f["geom_out"], ops.radar_geometry(t_f["ref_out"], y, pc, 1.0, 2.0, centre_is_normalised=True))
+
+    # ---- regression head + box anchor tail into a strided destination
+    keys = tuple(f"final_reg2.{i}" for i in (0, 2, 4))
+    anchor = rnd((M, 10), 7, 20.0)
+    out = torch.empty((3, M, 10), device=dev())[1]
+    plain = ops.mlp(x16, W(keys[0]), sd[keys[0] + ".bias"], W(keys[1]), sd[keys[1] + ".bias"], W(keys[2]), sd[keys[2] + ".bias"])
+    t_f = dict(kind="box", anchor=anchor, xy_col=0, z_col=4, from_norm=False, pc_range=pc, geom=(0.5, 1.0))
+    ops.mlp(x16, W(keys[0]), sd[keys[0] + ".bias"], W(keys[1]), sd[keys[1] + ".bias"], W(keys[2]), sd[keys[2] + ".bias"],
+            out_f32=out, tail=t_f)
+    want = O.lin(sd, keys[2], F.relu(O.lin(sd, keys[1], F.relu(O.lin(sd, keys[0], x)))))
+    torch.testing.assert_close(plain, want, rtol=2e-5, atol=2e-5)
+    boxed = ops.box_anchor_add(plain.clone(), anchor, 0, 4, False, pc)
+    assert torch.equal(out, boxed)
+    assert torch.equal(t_f["geom_out"], ops.radar_geometry(boxed, boxed, pc, 0.5, 1.0, centre_is_normalised=False))
+
+    # ---- classification head: Linear + LayerNorm + ReLU twice, then Linear
+    keys = tuple(f"final_cls.{i}" for i in (0, 3, 6))
+    lns = tuple((sd[f"final_cls.{i}.weight"], sd[f"final_cls.{i}.bias"]) for i in (1, 4))
+    y = ops.mlp(x16, W(keys[0]), sd[keys[0] + ".bias"], W(keys[1]), sd[keys[1] + ".bias"], W(keys[2]), sd[keys[2] + ".bias"],
+                ln1=lns[0], ln2=lns[1])
+    h1 = F.relu(O.lnorm(sd, "final_cls.1", O.lin(sd, keys[0], x)))
+    h2 = F.relu(O.lnorm(sd, "final_cls.4", O.lin(sd, keys[1], h1)))
+    # two LayerNorms in the chain amplify the ~1e-5 error of a bf16x3 product: 5e-5 against the fp32 oracle, while the
+    # fused and the three-launch path (same arithmetic, different summation order of the LayerNorm statistics) agree to 1e-5
+    torch.testing.assert_close(y, O.lin(sd, keys[2], h2), rtol=5e-5, atol=5e-5)
+    torch.testing.assert_close(y, unfused(keys, lns, None), rtol=1e-5, atol=1e-5)
+
+
+def test_mlp_bad_arguments(ops):
+    x = ops.cast_split(rnd((64, 256), 1))
+    W1, W3 = ops.cast_split(rnd((256, 256), 2)), ops.cast_split(rnd((10, 256), 3))
+    b, b3 = rnd((256,), 4), rnd((10,), 5)
+    with pytest.raises(RuntimeError, match="C = 256 and N3 <= 32"):
+        ops.mlp(x, W1, b, W1, b, ops.cast_split(rnd((64, 256), 6)), rnd((64,), 7))
+    with pytest.raises(RuntimeError, match="out_f32 has shape"):
+        ops.mlp(x, W1, b, W1, b, W3, b3, out_f32=torch.empty((64, 12), device=dev()))
+
+
 def test_linear_bad_arguments(ops):
     A, W = rnd((4, 8), 1), rnd((3, 8), 2)
     with pytest.raises(RuntimeError, match="CUDA tensor"):

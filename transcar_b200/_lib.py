@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtranscar_b200.so")
 
 TC_F32, TC_BF16, TC_BF16X2, TC_F16 = 0, 1, 2, 3
 TC_MAX_LEVELS, TC_MAX_CAMS = 4, 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 TC_SAMPLE_ALL_CAMS, TC_SAMPLE_WEIGHTS_GIVEN = 1, 2
 TC_TAIL_NONE, TC_TAIL_REF_UPDATE, TC_TAIL_BOX = 0, 1, 2
 TC_ATTN_AUTO, TC_ATTN_TENSOR, TC_ATTN_SIMT, TC_ATTN_SPARSE = 0, 1, 2, 3
@@ -56,6 +56,18 @@ class FfnArgs(C.Structure):
                 ("residual", _vp), ("ld_residual", _i64), ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_eps", _f32),
                 ("out_f32", _vp), ("ld_out_f32", _i64), ("out16", _vp), ("ld_out16", _i64),
                 ("M", _i32), ("C", _i32), ("H", _i32), ("w_static", _i32)]
+
+
+class MlpArgs(C.Structure):
+    _fields_ = [("X", _vp), ("ldx", _i64),
+                ("W1", _vp), ("ldw1", _i64), ("b1", _vp), ("ln1_gamma", _vp), ("ln1_beta", _vp),
+                ("W2", _vp), ("ldw2", _i64), ("b2", _vp), ("ln2_gamma", _vp), ("ln2_beta", _vp),
+                ("W3", _vp), ("ldw3", _i64), ("b3", _vp),
+                ("ln_eps", _f32), ("out_f32", _vp), ("ld_out_f32", _i64),
+                ("M", _i32), ("C", _i32), ("N3", _i32), ("w_static", _i32),
+                ("tail", _i32), ("tail_in", _vp), ("ld_tail_in", _i64), ("tail_ref_out", _vp), ("tail_geom_out", _vp),
+                ("tail_xy_col", _i32), ("tail_z_col", _i32), ("tail_from_norm", _i32),
+                ("tail_pc_range", _f32 * 6), ("tail_r_lo", _f32), ("tail_r_hi", _f32)]
 
 
 class PointEmbedArgs(C.Structure):
@@ -169,6 +181,7 @@ SYMBOLS = {
     "tc_nchw_to_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tc_linear": (C.c_int, [C.POINTER(LinearArgs), _vp]),
     "tc_ffn": (C.c_int, [C.POINTER(FfnArgs), _vp]),
+    "tc_mlp": (C.c_int, [C.POINTER(MlpArgs), _vp]),
     "tc_point_embed": (C.c_int, [C.POINTER(PointEmbedArgs), _vp]),
     "tc_attention_fwd": (C.c_int, [C.POINTER(AttentionArgs), _vp]),
     "tc_radar_geometry": (C.c_int, [C.POINTER(RadarGeometryArgs), _vp]),

@@ -35,6 +35,7 @@ RADIUS_CLAMP = ((1.0, 2.0), (1.0, 2.0), (0.5, 1.0))      # H:567, H:635, H:693
 # sampling kernel then shares SMs with the branch's remaining GEMM (it needs whole SMs: 192 KB rings) and its in-step
 # duration grows from 18.4 to 25.2 us - not worth it.
 _JOIN_FULL = not os.environ.get("TC_JOIN_SPLIT")
+_FUSE_MLP = not os.environ.get("TC_NO_MLP_FUSE")          # A/B: the fused three-layer heads (tc_mlp) vs three Linear launches
 _FUSE_FFN = not os.environ.get("TC_NO_FFN_FUSE")          # A/B: the fused feed-forward launch (tc_ffn) vs two Linear launches
 
 
@@ -197,6 +198,28 @@ class FusionDecoderEngine:
     def _ln(self, key):
         return (self.f32[key + ".weight"], self.f32[key + ".bias"])
 
+    def _mlp(self, x16, keys, lns=(None, None), out_f32=None, tail=None):
+        """Three-layer head ``keys = (k1, k2, k3)`` (Linear [+ LayerNorm] + ReLU twice, then Linear + optional row-local
+        tail): one fused launch in the bf16x3 mode (``tc_mlp``), else three Linear launches.  Returns the fp32 output."""
+        k1, k2, k3 = keys
+        w1, w2, w3 = (self.w[k + ".weight"] for k in keys)
+        ln1, ln2 = (self._ln(k) if k is not None else None for k in lns)
+        if _FUSE_MLP and self.x3 and ops.mlp_supported(x16, w1, w2, w3):
+            out = ops.mlp(x16, w1, self.f32[k1 + ".bias"], w2, self.f32[k2 + ".bias"], w3, self.f32[k3 + ".bias"],
+                          ln1=ln1, ln2=ln2, out_f32=out_f32, tail=tail)
+            self._keep.append(x16)
+            return out
+        a = self._lin(x16, k1, feed=True, relu=True, **({"ln": ln1} if ln1 is not None else {}))
+        b = self._lin(a, k2, feed=True, relu=True, **({"ln": ln2} if ln2 is not None else {}))
+        kw = {}
+        if out_f32 is not None:
+            kw["out_f32"] = out_f32
+        if tail is not None:
+            kw["tail"] = tail
+        out, _ = ops.linear(b, w3, self.f32[k3 + ".bias"], **kw)
+        self._keep.extend((x16, a, b))
+        return out
+
     def _ffn(self, x32, x16, key1, key2, norm):
         """x + W2 relu(W1 x) followed by LayerNorm (mmcv FFN + norm; H:583-586): one fused launch in the bf16x3 mode
         (``tc_ffn``), else two Linear launches."""
@@ -342,18 +365,17 @@ class FusionDecoderEngine:
             # layer's self-attention needs only x, so this chain (~45 us) hides behind in_proj + attention + out_proj.
             with self._branch(0):
                 if refine:
-                    r = self._lin(x16, f"reg_branches.{l}.0", feed=True, relu=True)
-                    r2 = self._lin(r, f"reg_branches.{l}.2", feed=True, relu=True)
-                    # last Linear of the refinement branch with the reference update (T:195-203) as its row-local tail; the
-                    # last layer's also emits the first radar layer's mask geometry (H:543-567)
+                    # refinement branch (Linear-ReLU-Linear-ReLU-Linear) with the reference update (T:195-203) as the
+                    # row-local tail of its last Linear; the last layer's also emits the first radar layer's mask
+                    # geometry (H:543-567)
                     tail = dict(kind="ref_update", ref=ref, pc_range=self.pc_range,
                                 geom=RADIUS_CLAMP[0] if (self.has_radar and l == self.L - 1) else None)
-                    code = self._lin(r2, f"reg_branches.{l}.4", tail=tail)
+                    code = self._mlp(x16, (f"reg_branches.{l}.0", f"reg_branches.{l}.2", f"reg_branches.{l}.4"), tail=tail)
                     ref = tail["ref_out"]
                     self._geom0 = tail.get("geom_out")
                     self._keep.append(self._geom0)
                     self._mark_ref()
-                    self._keep.extend((x16, r, r2, code, ref))
+                    self._keep.extend((x16, code, ref))
                 if l + 1 < self.L:
                     pos_feat = self._position_encoder(f"transformer.decoder.layers.{l + 1}.", ref)
             if keep_all or l == self.L - 1:
@@ -475,20 +497,15 @@ class FusionDecoderEngine:
                     qp_next = q_proj(li + 1, x16)
             with self._branch(0):      # classification head: independent of the regression head and of the next layer
                 # (starting it behind the regression head's wide GEMMs instead was measured: +3 us per step)
-                c = self._lin(x16, "final_cls" + m + ".0", feed=True, ln=self._ln("final_cls" + m + ".1"), relu=True)
-                c2 = self._lin(c, "final_cls" + m + ".3", feed=True, ln=self._ln("final_cls" + m + ".4"), relu=True)
-                ops.linear(c2, self.w["final_cls" + m + ".6.weight"], self.f32["final_cls" + m + ".6.bias"],
-                           out_f32=cls_all[li].view(M, n_cls))
-                self._keep.extend((c, c2, x16))
-            g = self._lin(x16, "final_reg" + m + ".0", feed=True, relu=True)
-            g = self._lin(g, "final_reg" + m + ".2", feed=True, relu=True)
+                self._mlp(x16, ("final_cls" + m + ".0", "final_cls" + m + ".3", "final_cls" + m + ".6"),
+                          lns=("final_cls" + m + ".1", "final_cls" + m + ".4"), out_f32=cls_all[li].view(M, n_cls))
             reg = reg_all[li].view(M, n_code)
             # last Linear of the regression head; tail = anchor update (li == 0, H:596-600: x,y of the refined reference in
             # metres, z left normalised - quirk Q3; else H:664-665 / H:722-723: previous stage's (cx, cy, cz) columns
             # 0, 1, 4) + the NEXT radar layer's mask geometry (H:615-635 / H:671-693)
             tail = dict(kind="box", anchor=anchor, xy_col=0, z_col=2 if li == 0 else 4, from_norm=li == 0,
                         pc_range=self.pc_range, geom=RADIUS_CLAMP[li + 1] if li + 1 < 3 else None)
-            ops.linear(g, self.w["final_reg" + m + ".4.weight"], self.f32["final_reg" + m + ".4.bias"], out_f32=reg, tail=tail)
+            self._mlp(x16, ("final_reg" + m + ".0", "final_reg" + m + ".2", "final_reg" + m + ".4"), out_f32=reg, tail=tail)
             aux[f"radar{li}.row_any"] = row_any
             aux[f"radar{li}.geom"] = geom
             geom = tail.get("geom_out")

@@ -256,21 +256,7 @@ def linear(A, W, bias=None, *, row_bias=None, row_bias_period=0, row_gate=None, 
             raise RuntimeError(f"transcar_b200.linear: 16-bit output has shape {tuple(o.shape)} for M, N = {(M, N)}")
         a.out_bf16, a.ld_out_bf16 = o.data_ptr(), ldo
     if tail is not None:
-        tin, ldt = _rows(_need(tail["ref" if tail["kind"] == "ref_update" else "anchor"], "tail_in", torch.float32), "tail_in")
-        keep.append(tin)
-        a.tail = _lib.TC_TAIL_REF_UPDATE if tail["kind"] == "ref_update" else _lib.TC_TAIL_BOX
-        a.tail_in, a.ld_tail_in = tin.data_ptr(), ldt
-        for i in range(6):
-            a.tail_pc_range[i] = float(tail["pc_range"][i])
-        if tail["kind"] == "ref_update":
-            tail["ref_out"] = torch.empty((M, 3), device=A.device, dtype=torch.float32)
-            a.tail_ref_out = tail["ref_out"].data_ptr()
-        else:
-            a.tail_xy_col, a.tail_z_col, a.tail_from_norm = tail["xy_col"], tail["z_col"], 1 if tail["from_norm"] else 0
-        if tail.get("geom") is not None:
-            tail["geom_out"] = torch.empty((M, 8), device=A.device, dtype=torch.float32)
-            a.tail_geom_out = tail["geom_out"].data_ptr()
-            a.tail_r_lo, a.tail_r_hi = float(tail["geom"][0]), float(tail["geom"][1])
+        _fill_tail(a, tail, M, A.device, keep)
     label = "linear" if TIMELINE is None else (
         f"linear M{M} N{N} K{K} {'bf16x3' if split else 'bf16' if A.dtype == torch.bfloat16 else 'f32'}" + ("+rb" if row_bias is not None else "") +
         ("+gate" if row_gate is not None else "") + ("+res" if residual is not None else "") +
@@ -319,6 +305,71 @@ def ffn(x, W1, b1, W2, b2, residual, ln, ln_eps=1e-5, want_f32=True, want_16=Tru
     label = "ffn" if TIMELINE is None else f"ffn M{M} C{Cc} H{H} bf16x3+res+ln"
     _lib.check(_call(label, lib.tc_ffn, C.byref(a), _stream()), "ffn")
     return o32, o16
+
+
+def mlp_supported(x, W1, W2, W3):
+    """True when ``tc_mlp`` (the fused three-layer head) covers these operands: split bf16, C = 256, at most 32 outputs."""
+    return (all(isinstance(t, SplitBf16) for t in (x, W1, W2, W3)) and x.shape[-1] == 256
+            and tuple(W1.shape) == (256, 256) and tuple(W2.shape) == (256, 256) and W3.shape[1] == 256 and W3.shape[0] <= 32)
+
+
+def _fill_tail(a, tail, M, device, keep):
+    """Shared by linear() and mlp(): the row-local tail fields of the argument block (see ``tc_linear``)."""
+    tin, ldt = _rows(_need(tail["ref" if tail["kind"] == "ref_update" else "anchor"], "tail_in", torch.float32), "tail_in")
+    keep.append(tin)
+    a.tail = _lib.TC_TAIL_REF_UPDATE if tail["kind"] == "ref_update" else _lib.TC_TAIL_BOX
+    a.tail_in, a.ld_tail_in = tin.data_ptr(), ldt
+    for i in range(6):
+        a.tail_pc_range[i] = float(tail["pc_range"][i])
+    if tail["kind"] == "ref_update":
+        tail["ref_out"] = torch.empty((M, 3), device=device, dtype=torch.float32)
+        a.tail_ref_out = tail["ref_out"].data_ptr()
+    else:
+        a.tail_xy_col, a.tail_z_col, a.tail_from_norm = tail["xy_col"], tail["z_col"], 1 if tail["from_norm"] else 0
+    if tail.get("geom") is not None:
+        tail["geom_out"] = torch.empty((M, 8), device=device, dtype=torch.float32)
+        a.tail_geom_out = tail["geom_out"].data_ptr()
+        a.tail_r_lo, a.tail_r_hi = float(tail["geom"][0]), float(tail["geom"][1])
+
+
+def mlp(x, W1, b1, W2, b2, W3, b3, ln1=None, ln2=None, ln_eps=1e-5, out_f32=None, tail=None):
+    """W3 f2(W2 f1(W1 x + b1) + b2) + b3 as ONE launch (``tc_mlp``, csrc/mlp_tc.cu); f = ReLU, or ReLU(LayerNorm(.)) when
+    ``ln1`` / ``ln2`` = (gamma, beta) is given.  x [M, 256], W1 / W2 [256, 256], W3 [N3 <= 32, 256] are :class:`SplitBf16`.
+    ``tail`` as in :func:`linear`.  Returns the fp32 [M, N3] output."""
+    lib = _lib.load()
+    if not mlp_supported(x, W1, W2, W3):
+        raise RuntimeError("transcar_b200.mlp: needs split-bf16 operands with C = 256 and N3 <= 32 (use three linear() calls)")
+    X, ldx = _rows(_need(x.t, "x"), "x")
+    w1, ldw1 = _rows(_need(W1.t, "W1"), "W1")
+    w2, ldw2 = _rows(_need(W2.t, "W2"), "W2")
+    w3, ldw3 = _rows(_need(W3.t, "W3"), "W3")
+    M, N3 = X.shape[0], w3.shape[0]
+    a = _lib.MlpArgs()
+    a.X, a.ldx, a.W1, a.ldw1, a.W2, a.ldw2, a.W3, a.ldw3 = (X.data_ptr(), ldx, w1.data_ptr(), ldw1, w2.data_ptr(), ldw2,
+                                                           w3.data_ptr(), ldw3)
+    a.b1 = _need(b1, "b1", torch.float32).data_ptr()
+    a.b2 = _need(b2, "b2", torch.float32).data_ptr()
+    a.b3 = _need(b3, "b3", torch.float32).data_ptr()
+    if ln1 is not None:
+        a.ln1_gamma, a.ln1_beta = _need(ln1[0], "ln1_gamma", torch.float32).data_ptr(), _need(ln1[1], "ln1_beta", torch.float32).data_ptr()
+    if ln2 is not None:
+        a.ln2_gamma, a.ln2_beta = _need(ln2[0], "ln2_gamma", torch.float32).data_ptr(), _need(ln2[1], "ln2_beta", torch.float32).data_ptr()
+    a.ln_eps = float(ln_eps)
+    a.M, a.C, a.N3 = M, 256, N3
+    a.w_static = 1 if (W1.static and W2.static and W3.static) else 0
+    if out_f32 is None:
+        out_f32 = torch.empty((M, N3), device=X.device, dtype=torch.float32)
+    o, ldo = _rows(_need(out_f32, "out_f32", torch.float32), "out_f32")
+    if o.shape != (M, N3):
+        raise RuntimeError(f"transcar_b200.mlp: out_f32 has shape {tuple(o.shape)}, expected {(M, N3)}")
+    a.out_f32, a.ld_out_f32 = o.data_ptr(), ldo
+    keep = [X, w1, w2, w3]
+    if tail is not None:
+        _fill_tail(a, tail, M, X.device, keep)
+    label = "mlp" if TIMELINE is None else (
+        f"mlp M{M} C256 N{N3} bf16x3" + ("+ln" if ln1 is not None or ln2 is not None else "") + (f"+tail:{tail['kind']}" if tail is not None else ""))
+    _lib.check(_call(label, lib.tc_mlp, C.byref(a), _stream()), "mlp")
+    return out_f32
 
 
 def point_embed(x, weight, bias, ln_gamma, ln_beta, logit_input, ln_eps=1e-5, want_f32=True, want_bf16=False,
