@@ -514,8 +514,16 @@ def run_infer(args):
         by_shape = {}
         for label, ms in zip(tl_labels, tl_ms):
             m = re.match(r"linear M(\d+) N(\d+) K(\d+) (bf16x3|bf16)", label)
+            fl = 2.0 * int(m.group(1)) * int(m.group(2)) * int(m.group(3)) if m else None
+            if not m:       # the fused launches: feed-forward block (C -> H -> C) and three-layer heads (C -> C -> C -> N3)
+                m = re.match(r"ffn M(\d+) C(\d+) H(\d+) ", label)
+                if m:
+                    fl = 2.0 * int(m.group(1)) * 2 * int(m.group(2)) * int(m.group(3))
+                else:
+                    m = re.match(r"mlp M(\d+) C(\d+) N(\d+) ", label)
+                    if m:
+                        fl = 2.0 * int(m.group(1)) * int(m.group(2)) * (2 * int(m.group(2)) + int(m.group(3)))
             if m:
-                fl = 2.0 * int(m.group(1)) * int(m.group(2)) * int(m.group(3))
                 lin_flops += fl
                 lin_ms += ms
                 lin_n += 1
@@ -540,7 +548,8 @@ def run_infer(args):
 
         worst = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]
         roofline_tensor = {
-            "linear": entry("linear_tc_kernel (K3: every tcgen05 Linear + fused epilogue of the step)", lin_flops, lin_ms, lin_n,
+            "linear": entry("linear_tc_kernel + ffn_tc_kernel + mlp_tc_kernel (K3: every tcgen05 Linear of the step, stand-alone or "
+                            "fused into a feed-forward block / three-layer head)", lin_flops, lin_ms, lin_n,
                             {"mma_passes": passes,
                              "executed_mma_frac": passes * (lin_flops / (lin_ms * 1e-3) / 1e12) / tpeak if lin_ms else 0,
                              "top_shapes": [{"call": k, "n": v[0], "avg_ms": v[1] / v[0],

@@ -1,5 +1,9 @@
 """Kernel timeline of one CUDA-graph replay of the step (CUPTI through torch.profiler): start / duration / stream per
 kernel, gaps and overlap.  Usage: python tools/step_trace.py [out.json] [precision]"""
+import re
+def _short(n):
+    n = n.replace("tc::(anonymous namespace)::", "").replace("void ", "")
+    return re.sub(r"\(.*", "", n)[:60]
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -35,4 +39,4 @@ for e in ev:
         cur_end = s + d
 print(f"time with at least one kernel running: {busy:.1f} us")
 for e in ev:
-    print(f"{e['ts'] - t0:9.1f} {e['dur']:7.1f} s{e['args'].get('stream', '?'):<4} {e['name'][:70]}")
+    print(f"{e['ts'] - t0:9.1f} {e['dur']:7.1f} s{e['args'].get('stream', '?'):<4} {_short(e['name'])}  grid {e['args'].get('grid', '?')}")

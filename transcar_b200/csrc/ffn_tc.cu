@@ -41,7 +41,7 @@ constexpr uint32_t kATile = BM * BK * 2;                       // 16 KB: 128 row
 constexpr uint32_t kWTile = 256 * BK * 2;                      // 32 KB: 256 rows x 64 bf16
 constexpr uint32_t kStageBytes = 2 * kATile + 2 * kWTile;      // A_hi | A_lo | W_hi | W_lo = 96 KB
 constexpr int kStages = 2;
-constexpr uint32_t kOffBars = kStages * kStageBytes;           // full[2], a2[2], empty[2], hbar, accbar, ringfree, xbar, tmem slot
+constexpr uint32_t kOffBars = kStages * kStageBytes;           // full[2], a2[2], empty[2], hbar, accbar, ringfree, xbar, ackbar, tmem slot
 constexpr uint32_t kOffVec = kOffBars + 128;                   // b1 (HH), b2 (OWN), gamma (OWN), beta (OWN)
 constexpr uint32_t kOffPart = kOffVec + (HH + 3 * OWN) * 4;    // LayerNorm partials: kSlots x BM x (sum, sum of squares)
 constexpr int kSlots = 4;                                      // (CTA, column half) contributors per row
@@ -65,25 +65,6 @@ struct FfnParams {
   unsigned long long* trace;   // tc_debug_trace: 16 uint64 per CTA, or null
 };
 
-// arrive on the same-offset mbarrier of CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-// bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into the same-layout shared memory of CTA `rank`;
-// completion is counted (complete_tx) on that CTA's mbarrier at offset `local_bar`
-__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_local, uint32_t src, uint32_t bytes, uint32_t local_bar, uint32_t rank) {
-  uint32_t rdst, rbar;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(dst_local), "r"(rank));
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(rdst), "r"(src), "r"(bytes), "r"(rbar) : "memory");
-}
-__device__ __forceinline__ void lds128(uint32_t addr, float* v) {
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
               const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_o32,
@@ -91,7 +72,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   float* s_b1 = reinterpret_cast<float*>(smem + kOffVec);
   float* s_b2 = s_b1 + HH;
   float* s_gamma = s_b2 + OWN;
@@ -100,7 +81,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), a20 = smem_u32(bars + 2), empty0 = smem_u32(bars + 4);
   const uint32_t hbar = smem_u32(bars + 6), accbar = smem_u32(bars + 7);
-  const uint32_t ringfree = smem_u32(bars + 8), xbar = smem_u32(bars + 9);
+  const uint32_t ringfree = smem_u32(bars + 8), xbar = smem_u32(bars + 9), ackbar = smem_u32(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                  // which half of the hidden dimension / of the output columns
@@ -117,6 +98,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     mbar_init(accbar, 1);
     mbar_init(ringfree, 1);              // arrived by the PARTNER once its MMAs have retired (its copy may then land here ...
     mbar_init(xbar, 1);                  // ... and this one counts the bytes of that copy)
+    mbar_init(ackbar, 1);                // arrived by the partner once THIS CTA's copy has landed there (its source is then idle)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(xbar, kXchgBytes);
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -293,9 +275,9 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       for (int i = 0; i < 4; ++i)
         bulk_copy_to_cluster(smem_base + kOffXchgIn + i * (kXchgBytes / 4), smem_base + kOffXchgOut + i * (kXchgBytes / 4),
                              kXchgBytes / 4, xbar, partner);
-      tma_store_commit();
     }
     mbar_wait(xbar, 0);                  // the partner's partial sums have landed here
+    if (threadIdx.x == 64) mbar_arrive_remote(ackbar, partner);
     if (threadIdx.x == 64) TC_TRACE(14);
 
     // ---- final rows: own partial + partner's + (bias + identity), LayerNorm over the 256 columns of the pair
@@ -345,8 +327,9 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 
     if (threadIdx.x == 64) TC_TRACE(15);
     // ---- outputs: swizzled staging tiles + TMA tile stores (rows beyond M are clipped), as in linear_tc.cu.  The staging
-    // tiles reuse the source of the outgoing copy: it has been read by now (the symmetric incoming copy has landed)
-    if (threadIdx.x == 64) tma_store_wait_read();
+    // tiles reuse the source of the outgoing copy: the partner acknowledges its arrival (a copy that completes on an
+    // mbarrier is not part of a bulk async-group, so wait_group cannot vouch for it); the wait is over long before
+    if (threadIdx.x == 64) mbar_wait(ackbar, 0);
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const int mrow = m0 + quad * 32;
 #pragma unroll

@@ -91,6 +91,8 @@ static __device__ __forceinline__ uint32_t cluster_nctarank() {
   return r;
 }
 static __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// (no memory ordering: for warps that publish nothing but mbarrier inits, which fence.mbarrier_init.release.cluster covers)
+static __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 static __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // LayerNorm statistics exchange between the CTAs of a cluster: every CTA PUSHES its per-row (sum, sum of squares) into
 // slot [own rank][row] of each peer's shared memory (one relaxed 64-bit store: the value is its own flag, nothing else is
@@ -108,6 +110,26 @@ static __device__ __forceinline__ unsigned long long ld_smem_u64(uint32_t addr) 
   unsigned long long v;
   asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
   return v;
+}
+
+// ---- cluster pair helpers of the fused kernels (ffn_tc.cu) ------------------------------------------------
+// arrive on the same-offset mbarrier of CTA `rank` of the cluster
+static __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into the same-layout shared memory of CTA `rank`;
+// completion is counted (complete_tx) on that CTA's mbarrier at offset `local_bar`
+static __device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_local, uint32_t src, uint32_t bytes, uint32_t local_bar, uint32_t rank) {
+  uint32_t rdst, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(dst_local), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(rdst), "r"(src), "r"(bytes), "r"(rbar) : "memory");
+}
+static __device__ __forceinline__ void lds128(uint32_t addr, float* v) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
 }
 
 }  // namespace tc
