@@ -5,8 +5,10 @@
 // (~260 of 900 queries have any key at all, most of those one to five).  A dense-tile kernel
 // (attention_tc.cu / attention_simt.cu) spends all of its time on pairs whose probability is exactly zero and
 // re-derives the same mask once per head.  This kernel does the necessary work only:
-//   * one warp per (sample, query), 16 queries per CTA; every lane owns 8 consecutive channels of the 256-wide embedding, so a head
-//     (32 channels) is a group of 4 lanes and all 8 heads share ONE pass over the keys;
+//   * one warp per (sample, query), 8 queries per CTA, four CTAs per SM (64 registers: at 98 registers and 16 warps a
+//     single CTA fitted an SM and the 456-CTA grid ran as three waves - 21.2 -> 16.1 us per launch); every lane owns 8
+//     consecutive channels of the 256-wide embedding, so a head (32 channels) is a group of 4 lanes and all 8 heads share
+//     ONE pass over the keys;
 //   * scan: 32 keys per iteration, one key per lane, a conservative squared-distance prefilter (5 instructions);
 //     only candidates run the exact test, which is bit-identical to torch.cdist's mm route (tc_common.cuh);
 //   * for each allowed key (rare): one 512-byte K row and V row read (16 B per lane), per-head dot product reduced
@@ -17,7 +19,7 @@
 namespace tc {
 namespace {
 
-constexpr int kWarps = 16;
+constexpr int kWarps = 8;
 
 struct SparseParams {
   const void* q; const void* k; const void* v;
@@ -47,7 +49,7 @@ __device__ __forceinline__ void load8(const void* base, long long off, float (&d
 constexpr int kKeyTile = 2048;           // keys staged in shared memory per pass (x, y, |k|^2: 24 KB)
 
 template <bool kBf16In, bool kBf16Out>
-__global__ void __launch_bounds__(kWarps * 32) attention_sparse_kernel(const SparseParams p) {
+__global__ void __launch_bounds__(kWarps * 32, 4) attention_sparse_kernel(const SparseParams p) {
   __shared__ float2 s_kxy[kKeyTile];
   __shared__ float s_kn[kKeyTile];
   const int lane = threadIdx.x & 31;
