@@ -571,7 +571,7 @@ def run_infer(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE_NAME[args.precision], "data": "synthetic", "config": workload_config(args),
             "step": {"forward_ms": fwd_only_ms, "decode_gather_ms": ms_per_step - fwd_only_ms,
-                     "what": "forward (one CUDA graph) -> tc_decode records -> " +
+                     "what": "forward + tc_decode records (one CUDA graph; forward_ms includes the decode launch) -> output copies -> " +
                              ("NCCL all_gather_into_tensor of the records" if world > 1 else "(no gather at N=1)"),
                      "gather_bytes_per_rank": B * coder.max_num * sharding.RECORD_WIDTH * 4},
             "roofline": roofline, "roofline_tensor": roofline_tensor,

@@ -62,6 +62,7 @@ class FusionDecoderEngine:
         self.use_branches = True         # run independent sub-chains on side streams (parallel graph branches)
         self._side = None
         self._keep = []                  # tensors that cross streams stay referenced until the forward ends
+        self.graph_epilogue = None       # callable(out dict) -> tensor, captured behind the forward in the step graph ("records")
         self._graphs = {}
         self._init_cache = {}
         self._pinned = {}                # host staging buffers (pinned once, reused every forward)
@@ -578,14 +579,19 @@ class FusionDecoderEngine:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self._forward_eager(static)
+                if self.graph_epilogue is not None:       # e.g. the NMS-free decode: its launch joins the step graph
+                    out["records"] = self.graph_epilogue(out)
             entry = self._graphs[key] = (graph, s_l2i, s_tok, s_xy, out)
         graph, s_l2i, s_tok, s_xy, out = entry
         s_l2i.copy_(l2i, non_blocking=True)
         s_tok.copy_(tokens, non_blocking=True)
         s_xy.copy_(key_xy, non_blocking=True)
         graph.replay()
-        return dict(all_cls_scores=out["all_cls_scores"].clone(), all_bbox_preds=out["all_bbox_preds"].clone(),
-                    enc_cls_scores=None, enc_bbox_preds=None)
+        ret = dict(all_cls_scores=out["all_cls_scores"].clone(), all_bbox_preds=out["all_bbox_preds"].clone(),
+                   enc_cls_scores=None, enc_bbox_preds=None)
+        if "records" in out:
+            ret["records"] = out["records"].clone()
+        return ret
 
     @torch.no_grad()
     def capture_instrumented(self, prepared):

@@ -407,6 +407,8 @@ class NMSFreeCoder:
         what ``sharding.gather_results`` ships between ranks (no host sync, no pickling)."""
         if self.post_center_range is None:
             raise NotImplementedError("Need to reorganize output as a batch, only support post_center_range is not None for now!")
+        if preds_dicts.get("records") is not None:        # decoded inside the engine's step graph (Detr3DHead.engine())
+            return preds_dicts["records"]
         rec = ops.decode(preds_dicts["all_cls_scores"][-1], preds_dicts["all_bbox_preds"][-1], self.max_num,
                          self.post_center_range, records=True)
         if self.score_threshold:
