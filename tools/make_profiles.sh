@@ -5,7 +5,7 @@ R=${1:-r02}
 mkdir -p profiles
 python tools/launch_summary.py gpurun_out/launches.csv > profiles/${R}_launches_summary.txt
 cp gpurun_out/launches.csv profiles/${R}_launches_step.csv
-for k in sample attn linear attn_sparse; do
+for k in sample attn linear attn_sparse ffn mlp; do
   [ -f gpurun_out/prof_$k.ncu-rep ] && python tools/ncu_metrics.py gpurun_out/prof_$k.ncu-rep pipe_xu.avg.pct_of_peak_sustained_active lts__t_bytes.sum l1tex__m_xbar2l1tex_read_bytes.sum lts__throughput.avg.pct > profiles/${R}_ncu_$k.txt
 done
 [ -f gpurun_out/prof_sample.ncu-rep ] && python tools/ncu_traffic.py gpurun_out/prof_sample.ncu-rep profiles/${R}_k1_traffic.json > /dev/null
