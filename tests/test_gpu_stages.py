@@ -365,6 +365,21 @@ def test_mlp_bad_arguments(ops):
         ops.mlp(x, W1, b, W1, b, W3, b3, out_f32=torch.empty((64, 12), device=dev()))
 
 
+@pytest.mark.parametrize("M,N,K,relu", [(12000, 1536, 256, False), (2100, 1024, 128, True)])
+def test_linear_wide_tile_variant(ops, M, N, K, relu):
+    """Plain large-N bf16x3 products with an fp32 output take the 128 x 256-tile kernel (csrc/linear_wide_tc.cu: the stacked
+    radar K / V projection, H:578 / H:646 / H:704): vs fp32 matmul, including a partial last row block and a strided output."""
+    A, W, b = rnd((M, K), 31), rnd((N, K), 32, K ** -0.5), rnd((N,), 33, 0.1)
+    out = torch.zeros((M, N + 64), device=dev())[:, :N]                   # row pitch larger than N
+    y, _ = ops.linear(ops.cast_split(A), ops.mark_static(ops.cast_split(W)), b, relu=relu, out_f32=out)
+    want = A @ W.t() + b
+    if relu:
+        want = want.relu()
+    # bf16x3 keeps ~16 mantissa bits per operand: 18 M outputs of magnitude up to 5 -> the worst of them is 2.6e-5 off
+    torch.testing.assert_close(y, want, rtol=2e-5, atol=5e-5)
+    assert y.data_ptr() == out.data_ptr()
+
+
 def test_linear_bad_arguments(ops):
     A, W = rnd((4, 8), 1), rnd((3, 8), 2)
     with pytest.raises(RuntimeError, match="CUDA tensor"):

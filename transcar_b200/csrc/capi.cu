@@ -35,6 +35,8 @@ bool pdl_enabled() {
 
 int linear_simt_launch(const tc_linear_args* a, cudaStream_t s);
 int attention_simt_launch(const tc_attention_args* a, cudaStream_t s);
+bool linear_wide_supported(const tc_linear_args* a);
+int linear_wide_launch(const tc_linear_args* a, cudaStream_t s);
 bool linear_tc_supported(const tc_linear_args* a);
 int linear_tc_launch(const tc_linear_args* a, cudaStream_t s);
 bool attention_tc_supported(const tc_attention_args* a);
@@ -100,6 +102,7 @@ extern "C" int tc_linear(const tc_linear_args* a, tc_stream_t stream) {
   }
   if (a->M == 0) return TC_OK;
   cudaStream_t s = as_stream(stream);
+  if (linear_wide_supported(a)) return linear_wide_launch(a, s);
   if (linear_tc_supported(a)) return linear_tc_launch(a, s);
   return linear_simt_launch(a, s);
 }
