@@ -378,6 +378,16 @@ def test_linear_wide_tile_variant(ops, M, N, K, relu):
     # bf16x3 keeps ~16 mantissa bits per operand: 18 M outputs of magnitude up to 5 -> the worst of them is 2.6e-5 off
     torch.testing.assert_close(y, want, rtol=2e-5, atol=5e-5)
     assert y.data_ptr() == out.data_ptr()
+    if relu:
+        return
+    # per-query row bias + fp16 / bf16 output (the self-attention in-projection's epilogue), no fp32 copy
+    rb = rnd((900, N), 34, 0.5)
+    want = A @ W.t() + rb.repeat((M + 899) // 900, 1)[:M]
+    for out16, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+        y32, y16 = ops.linear(ops.cast_split(A), ops.mark_static(ops.cast_split(W)), None, row_bias=rb, row_bias_period=900,
+                              want_f32=False, want_bf16=True, out16=out16)
+        assert y32 is None and y16.dtype == dt
+        torch.testing.assert_close(y16.float(), want.to(dt).float(), rtol=2 ** -9 if dt == torch.float16 else 2 ** -6, atol=1e-3)
 
 
 def test_linear_bad_arguments(ops):
