@@ -63,6 +63,7 @@ class FusionDecoderEngine:
         self._side = None
         self._keep = []                  # tensors that cross streams stay referenced until the forward ends
         self.graph_epilogue = None       # callable(out dict) -> tensor, captured behind the forward in the step graph ("records")
+        self._own_inputs = set()         # addresses of the persistent device buffers of prepare_inputs (graphs read them in place)
         self._graphs = {}
         self._init_cache = {}
         self._pinned = {}                # host staging buffers (pinned once, reused every forward)
@@ -269,16 +270,20 @@ class FusionDecoderEngine:
         key = (name, tuple(shape))
         ent = self._pinned.get(key)
         if ent is None:
-            ent = self._pinned[key] = [torch.empty(shape, dtype=torch.float32).pin_memory(), None]
+            ent = self._pinned[key] = [torch.empty(shape, dtype=torch.float32).pin_memory(), None,
+                                       torch.empty(shape, dtype=torch.float32, device=self.device)]
+            self._own_inputs.add(ent[2].data_ptr())
         if ent[1] is not None:
             ent[1].synchronize()
         return ent
 
     def _upload(self, ent):
-        dev = ent[0].to(self.device, non_blocking=True)
+        """Pinned host buffer -> its PERSISTENT device twin (stable address: the step graph reads it in place, so a frame costs
+        one H2D copy per small input and no device-side staging copy)."""
+        ent[2].copy_(ent[0], non_blocking=True)
         ent[1] = torch.cuda.Event()
         ent[1].record()
-        return dev
+        return ent[2]
 
     def _prep_metas(self, img_metas, B):
         ent = self._staging("l2i", (B, self.N, 4, 4))
@@ -463,8 +468,12 @@ class FusionDecoderEngine:
         n_code = self.f32["final_reg.4.weight"].shape[0]           # code_size: the radar geometry / anchor columns need 10
         if n_code != 10:
             raise RuntimeError(f"transcar_b200: code_size must be 10 (got {n_code}): H:543-567 / H:596-600 index columns 0-7")
-        cls_all = torch.empty((3, B, Q, n_cls), device=self.device, dtype=torch.float32)
-        reg_all = torch.empty((3, B, Q, n_code), device=self.device, dtype=torch.float32)
+        if n_cls == n_code:           # one allocation: the graph path copies both out of its pool with a single launch
+            both = torch.empty((2, 3, B, Q, n_cls), device=self.device, dtype=torch.float32)
+            cls_all, reg_all = both[0], both[1]
+        else:
+            cls_all = torch.empty((3, B, Q, n_cls), device=self.device, dtype=torch.float32)
+            reg_all = torch.empty((3, B, Q, n_code), device=self.device, dtype=torch.float32)
         anchor, centre_norm = ref, True
         aux = {}
 
@@ -519,7 +528,9 @@ class FusionDecoderEngine:
     # ------------------------------------------------------------------ whole head (a8)
     def prepare_inputs(self, mlvl_feats, img_metas, radar=None):
         """Host -> device staging of one batch: feature layout/dtype hand-off, lidar2img (float64 -> fp32,
-        T:384-386), padded radar tokens (H:526-530).  Returns the tuple ``forward_prepared`` consumes."""
+        T:384-386), padded radar tokens (H:526-530).  Returns the tuple ``forward_prepared`` consumes.  The small per-frame
+        tensors of the tuple are the engine's persistent device buffers (stable addresses: the step graph reads them in place);
+        they are overwritten by the next ``prepare_inputs`` of the same batch size."""
         B = mlvl_feats[0].shape[0]
         if len(img_metas) != B:
             raise ValueError(f"img_metas has {len(img_metas)} entries for a batch of {B}")
@@ -569,7 +580,9 @@ class FusionDecoderEngine:
         if entry is None:
             if len(self._graphs) >= 8:
                 self._graphs.clear()
-            s_l2i, s_tok, s_xy = l2i.clone(), tokens.clone(), key_xy.clone()
+            # small per-frame inputs: the engine's own persistent buffers (prepare_inputs) are read in place; foreign tensors
+            # are copied into private static twins before every replay
+            s_l2i, s_tok, s_xy = (t if t.data_ptr() in self._own_inputs else t.clone() for t in (l2i, tokens, key_xy))
             static = (feats, s_l2i, img_w, img_h, s_tok, s_xy)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
@@ -583,12 +596,18 @@ class FusionDecoderEngine:
                     out["records"] = self.graph_epilogue(out)
             entry = self._graphs[key] = (graph, s_l2i, s_tok, s_xy, out)
         graph, s_l2i, s_tok, s_xy, out = entry
-        s_l2i.copy_(l2i, non_blocking=True)
-        s_tok.copy_(tokens, non_blocking=True)
-        s_xy.copy_(key_xy, non_blocking=True)
+        for st, t in ((s_l2i, l2i), (s_tok, tokens), (s_xy, key_xy)):
+            if st.data_ptr() != t.data_ptr():
+                st.copy_(t, non_blocking=True)
         graph.replay()
-        ret = dict(all_cls_scores=out["all_cls_scores"].clone(), all_bbox_preds=out["all_bbox_preds"].clone(),
-                   enc_cls_scores=None, enc_bbox_preds=None)
+        # the two score / box tensors are views of one allocation (radar_layers): one copy out of the graph's private pool
+        both = out["all_cls_scores"]._base
+        if both is not None and both is out["all_bbox_preds"]._base and out["all_cls_scores"].shape == out["all_bbox_preds"].shape:
+            both = both.clone()
+            ret = dict(all_cls_scores=both[0], all_bbox_preds=both[1], enc_cls_scores=None, enc_bbox_preds=None)
+        else:
+            ret = dict(all_cls_scores=out["all_cls_scores"].clone(), all_bbox_preds=out["all_bbox_preds"].clone(),
+                       enc_cls_scores=None, enc_bbox_preds=None)
         if "records" in out:
             ret["records"] = out["records"].clone()
         return ret
