@@ -36,6 +36,7 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     flags = FLAGS + (["-DTC_TRACE_BUILD"] if os.environ.get("TC_TRACE_BUILD") else [])   # tools/linear_trace.py marks
+    flags = flags + (["-DTC_SANITIZER_BUILD"] if os.environ.get("TC_SANITIZER_BUILD") else [])   # unbounded mbarrier spins
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

@@ -6,7 +6,13 @@
 
 namespace tc {
 
+// bounded spins turn a protocol bug into a trap instead of a hung GPU.  compute-sanitizer slows the kernels by orders of
+// magnitude: build with TC_SANITIZER_BUILD=1 (python -m transcar_b200.build --force) to lift the bound for such runs.
+#ifdef TC_SANITIZER_BUILD
+constexpr uint32_t kSpinLimit = 0xffffffffu;
+#else
 constexpr uint32_t kSpinLimit = 1u << 22;
+#endif
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -45,7 +51,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_test_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
+    if (++spins > kSpinLimit) __trap();      // (never with the sanitizer build: ++spins wraps before it exceeds 2^32 - 1)
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
