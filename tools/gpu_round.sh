@@ -16,7 +16,7 @@ timeout 300 python tools/step_trace.py gpurun_out/step_trace.json bf16x3 > gpuru
 timeout 300 python tools/step_timeline.py 20 bf16x3 > gpurun_out/step_timeline.log 2>&1; echo "timeline rc=$?"
 timeout 300 python tools/k1_bench.py > gpurun_out/k1_bench.log 2>&1; tail -1 gpurun_out/k1_bench.log
 (timeout 300 python tools/attn_bench.py 8; timeout 300 python tools/attn_bench.py 8 f16) > gpurun_out/attn_bench.log 2>&1; tail -2 gpurun_out/attn_bench.log
-(timeout 300 python tools/linear_bench.py 24; timeout 200 python tools/ffn_bench.py 24; timeout 300 python tools/sparse_attn_bench.py 20 2>&1 | grep "radar layer") > gpurun_out/linear_bench.log 2>&1; tail -5 gpurun_out/linear_bench.log
+(timeout 300 python tools/linear_bench.py 24; timeout 200 python tools/ffn_bench.py 24; timeout 200 python tools/mlp_bench.py 24; timeout 300 python tools/sparse_attn_bench.py 20 2>&1 | grep "radar layer"; timeout 200 python tools/replay_cost.py 2>&1 | tail -2) > gpurun_out/linear_bench.log 2>&1; tail -5 gpurun_out/linear_bench.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py 1 bf16x3 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 bash tools/gpu_ncu.sh sample:sample_kernel:2:1 attn:attention_tc:2:1 linear:linear_tc:12:9 attn_sparse:attention_sparse:1:1 ffn:ffn_tc:2:1 mlp:mlp_tc:2:2
 ls -la gpurun_out | head -60
