@@ -72,6 +72,29 @@ def test_argument_validation_without_gpu():
     at.D = 64
     assert lib.tc_attention_fwd(ctypes.byref(at), None) == -2
     assert b"head dim" in lib.tc_last_error_string()
+    # the fused launches validate before they touch the device: NULL blocks / pointers, unsupported sizes, misalignment
+    assert lib.tc_ffn(None, None) == -1 and lib.tc_mlp(None, None) == -1
+    f = _lib.FfnArgs()
+    assert lib.tc_ffn(ctypes.byref(f), None) == -1 and b"required" in lib.tc_last_error_string()
+    big = (ctypes.c_float * 64)()
+    base = (ctypes.addressof(big) + 31) & ~31
+    for name in ("X", "W1", "b1", "W2", "b2", "residual", "ln_gamma", "ln_beta", "out_f32"):
+        setattr(f, name, base)
+    f.M, f.C, f.H = 128, 128, 512
+    assert lib.tc_ffn(ctypes.byref(f), None) == -2 and b"C = 256, H = 512" in lib.tc_last_error_string()
+    f.C, f.ldx, f.ldw1, f.ldw2, f.ld_residual, f.ld_out_f32 = 256, 512, 512, 1024, 256, 256
+    f.X = base + 2
+    assert lib.tc_ffn(ctypes.byref(f), None) == -3 and b"16-byte aligned" in lib.tc_last_error_string()
+    m = _lib.MlpArgs()
+    for name in ("X", "W1", "b1", "W2", "b2", "W3", "b3", "out_f32"):
+        setattr(m, name, base)
+    m.M, m.C, m.N3 = 128, 256, 48
+    assert lib.tc_mlp(ctypes.byref(m), None) == -2 and b"N3 <= 32" in lib.tc_last_error_string()
+    m.N3, m.ldx, m.ldw1, m.ldw2, m.ldw3, m.ld_out_f32 = 10, 512, 512, 512, 512, 10
+    m.ln1_gamma = base                                                    # gamma without beta
+    assert lib.tc_mlp(ctypes.byref(m), None) == -1 and b"pairs" in lib.tc_last_error_string()
+    m.ln1_gamma, m.tail = None, _lib.TC_TAIL_BOX                          # a tail without its input
+    assert lib.tc_mlp(ctypes.byref(m), None) == -1 and b"tail" in lib.tc_last_error_string()
 
 
 def test_plugin_builds_from_reference_config_and_loads_reference_keys():
