@@ -13,7 +13,7 @@ done
 [ -f gpurun_out/prof_attn.ncu-rep ] && python tools/ncu_source.py gpurun_out/prof_attn.ncu-rep 1.0 > profiles/${R}_ncu_attn_source_lines.txt
 grep -v "UserWarning\|_warn_once" gpurun_out/step_trace.txt > profiles/${R}_step_trace_cupti.txt
 cp gpurun_out/step_timeline.log profiles/${R}_step_timeline.txt
-for f in bench bench_ref bench_bf16_onepass bench_vovnet bench_train_1gpu bench_train_unfrozen_1gpu bench_full_1gpu \
+for f in bench bench_ref bench_4gpu bench_bf16_onepass bench_vovnet bench_train_1gpu bench_train_unfrozen_1gpu bench_full_1gpu \
          bench_2gpu bench_8gpu bench_vovnet_8gpu bench_train_2gpu bench_train_8gpu bench_train_unfrozen_8gpu bench_full_8gpu; do
   [ -f gpurun_out/$f.json ] && grep "^{" gpurun_out/$f.json | tail -1 > profiles/${R}_$f.json
 done
