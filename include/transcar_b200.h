@@ -182,8 +182,8 @@ TC_API int tc_linear(const tc_linear_args* a, tc_stream_t stream);
 
 /* Fused feed-forward block in the bf16x3 operand format:  Y = LayerNorm(residual + W2 relu(W1 X + b1) + b2).
  * Replaces the mmcv FFN + norm of a decoder layer (BaseTransformerLayer 'ffn', 'norm': ffns.0.layers.0.0 / layers.1 +
- * norms.2, configured at projects/configs/detr3d/detr3d_res101_gridmask.py:76-84) and H:583-586 (rf_linear2(relu(
- * rf_linear1(x))) + rf_norm3) - the same result as two tc_linear calls (relu, then residual + LayerNorm), as one launch
+ * norms.2, configured at projects/configs/detr3d/detr3d_res101_gridmask.py:65-82: feedforward_channels = 512, operation_order
+ * (..., 'ffn', 'norm')) and H:583-586 / H:655-658 / H:713-716 (rf_linear2(relu(rf_linear1(x))) + rf_norm3; modules at H:131-137) - the same result as two tc_linear calls (relu, then residual + LayerNorm), as one launch
  * in which the [M, H] hidden activation never leaves the SM pair that produced it (csrc/ffn_tc.cu).
  * X [M, 2C], W1 [H, 2C], W2 [C, 2H] are split bf16 (TC_BF16X2: hi | lo), residual fp32 [M, C] (the identity branch, normally
  * X in fp32).  Outputs: out_f32 [M, C] and / or out16 split bf16 [M, 2C]; either may be NULL.  Built for C = 256, H = 512 (the
@@ -204,8 +204,9 @@ TC_API int tc_ffn(const tc_ffn_args* a, tc_stream_t stream);
 /* Fused three-layer head in the bf16x3 operand format:  Y = W3 f2(W2 f1(W1 X + b1) + b2) + b3 with f = ReLU, or
  * ReLU(LayerNorm(.)) when that layer's ln gamma / beta are given, followed by the row-local tail of tc_linear
  * (TC_TAIL_REF_UPDATE / TC_TAIL_BOX on the first 8 output columns; same tail_* fields).  Replaces the three tc_linear launches
- * of reg_branches[l] (Linear-ReLU-Linear-ReLU-Linear, H:141-152; used at T:190-203), final_reg* (H:588-600, H:660-665,
- * H:718-723) and final_cls* (Linear-LN-ReLU-Linear-LN-ReLU-Linear, H:128-139): the two hidden activations stay in tensor /
+ * of reg_branches[l] (Linear-ReLU-Linear-ReLU-Linear, built at H:208-213 / H:224-225; used at T:190-203), final_reg* (built
+ * at H:84-90 / H:102-108 / H:120-126; used with the anchor add at H:593-600, H:662-665, H:720-723) and final_cls*
+ * (Linear-LN-ReLU-Linear-LN-ReLU-Linear, H:74-83 / H:92-101 / H:110-119; used at H:592, H:661, H:719): the two hidden activations stay in tensor /
  * shared memory of the CTA that owns the 128 rows (csrc/mlp_tc.cu).  X [M, 2C], W1 / W2 [C, 2C], W3 [N3, 2C] are split bf16;
  * out_f32 [M, N3] fp32.  Built for C = 256, N3 <= 32; other sizes return TC_ERR_SHAPE (callers use three tc_linear calls). */
 typedef struct {

@@ -1,8 +1,9 @@
 // K3f fused feed-forward block on tcgen05:  Y = LayerNorm(X + W2 relu(W1 X + b1) + b2)  for C = 256, H = 512 in the bf16x3
 // operand format (split bf16, three tensor-core passes per product, fp32 accumulation in tensor memory).
 //
-// Replaces two dependent tc_linear launches (mmcv FFN of the decoder layers, T:84-97 via the config's ffn_cfgs, and the
-// radar head's rf_linear1 / rf_linear2 + rf_norm3, H:583-586).  Unfused, the [M, 512] hidden activation makes a round trip
+// Replaces two dependent tc_linear launches (mmcv FFN + norm of the decoder layers: 'ffn', 'norm' of the operation_order at
+// projects/configs/detr3d/detr3d_res101_gridmask.py:65-82, and the radar head's rf_linear1 / rf_linear2 + rf_norm3, H:583-586 /
+// H:655-658 / H:713-716).  Unfused, the [M, 512] hidden activation makes a round trip
 // through L2 in split form (14.7 MB written, re-read once per 64-column output tile) and the second GEMM cannot start
 // before the last tile of the first has left: 12.8 + 14.4 us back to back at M = 7200.  Here a 128-row block never
 // leaves the SM pair that owns it:

@@ -2,9 +2,10 @@
 //     Y = W3 f2(W2 f1(W1 X + b1) + b2) + b3,   f = ReLU or ReLU(LayerNorm(.)),   C = 256 wide, N3 <= 32 outputs,
 // followed by the row-local tails of tc_linear (reference-point update / box anchor + next radar-mask geometry).
 //
-// Replaces the three dependent tc_linear launches of the refinement branches (reg_branches.l.{0,2,4}: T:190-203), of the radar
-// head's regression heads (final_reg*.{0,2,4}: H:588-600, H:660-665, H:718-723) and classification heads
-// (final_cls*.{0,1,3,4,6}: Linear + LayerNorm + ReLU twice, then Linear).  A 128-row block stays inside one CTA: the hidden
+// Replaces the three dependent tc_linear launches of the refinement branches (reg_branches.l.{0,2,4}: built at H:208-213, used
+// at T:190-203), of the radar head's regression heads (final_reg*.{0,2,4}: H:84-90 / 102-108 / 120-126, used at H:593-600,
+// H:662-665, H:720-723) and classification heads (final_cls*.{0,1,3,4,6}: Linear + LayerNorm + ReLU twice, then Linear;
+// H:74-83 / 92-101 / 110-119, used at H:592, H:661, H:719).  A 128-row block stays inside one CTA: the hidden
 // activations live in tensor memory (two 256-column accumulators), are turned - bias, optional LayerNorm over the row, ReLU,
 // hi / lo split - 64 columns at a time into the swizzled K-major A tiles of the next GEMM in shared memory, and only the
 // [M, N3] result leaves the SM.  Unfused, each hidden activation made a round trip through L2 in split form (7.4 MB written,
